@@ -1,0 +1,472 @@
+// C ABI of the ray-march path (include/kpnerf_b200.h): context, weight packer, scene packer,
+// render / query drivers.  Host logic only; kernels live in kpn_kernels.cu (fp32 SIMT engine)
+// and kpn_tc.cu (tensor-core engine).
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "kpn_launch.h"
+
+using namespace kpn;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int MAX_CHUNKS = 2048;
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct kpn_ctx {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  bool have_weights = false, have_scene = false;
+  int n_kpt = 0;
+  int sp_level = 3;
+  float sp_scale = 1.0f, sp_sigma = 0.1f;
+
+  RawScene* d_raw_scene = nullptr;
+  DevScene* d_scene = nullptr;
+  RawTarget* d_raw_target = nullptr;
+  DevTarget* d_target = nullptr;
+  DevWeightsF32* d_wf32 = nullptr;
+  DevBuf wbuf;
+  int* d_counters = nullptr;   // [MAX_CHUNKS]
+  int counters_used = 0;
+  unsigned long long last_total = 0;
+
+  DevBuf stage[4];             // host-sourced maps before packing
+  DevBuf atlas[4];             // f64, f8, ftex, img (channel-last fp32)
+  DevBuf atlas_fg;
+  DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in;
+  unsigned long long launches = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
+  size_t ev_used = 0;
+};
+
+#define KPN_FAIL(ctx, code, ...)                                   \
+  do {                                                             \
+    char _b[512];                                                  \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);                         \
+    (ctx)->err = _b;                                               \
+    return (code);                                                 \
+  } while (0)
+
+#define KPN_CUDA(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) KPN_FAIL(ctx, KPN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" int kpn_abi_version(void) { return KPN_ABI_VERSION; }
+
+extern "C" int kpn_create(int device, kpn_ctx** out) {
+  if (!out) return KPN_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return KPN_ERR_CUDA;  // no CPU fallback
+  if (device < 0 || device >= ndev) return KPN_ERR_ARG;
+  kpn_ctx* c = new kpn_ctx();
+  c->device = device;
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return KPN_ERR_CUDA; }
+  c->num_sms = prop.multiProcessorCount;
+  bool ok = cudaMalloc(&c->d_raw_scene, sizeof(RawScene)) == cudaSuccess &&
+            cudaMalloc(&c->d_scene, sizeof(DevScene)) == cudaSuccess &&
+            cudaMalloc(&c->d_raw_target, sizeof(RawTarget)) == cudaSuccess &&
+            cudaMalloc(&c->d_target, sizeof(DevTarget)) == cudaSuccess &&
+            cudaMalloc(&c->d_wf32, sizeof(DevWeightsF32)) == cudaSuccess &&
+            cudaMalloc(&c->d_counters, sizeof(int) * MAX_CHUNKS) == cudaSuccess;
+  if (!ok) { kpn_destroy(c); return KPN_ERR_CUDA; }
+  cudaMemset(c->d_counters, 0, sizeof(int) * MAX_CHUNKS);
+  *out = c;
+  return KPN_OK;
+}
+
+extern "C" void kpn_destroy(kpn_ctx* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  cudaFree(c->d_raw_scene); cudaFree(c->d_scene); cudaFree(c->d_raw_target); cudaFree(c->d_target);
+  cudaFree(c->d_wf32); cudaFree(c->d_counters);
+  c->wbuf.release();
+  for (auto& b : c->stage) b.release();
+  for (auto& b : c->atlas) b.release();
+  c->atlas_fg.release();
+  c->ws_z.release(); c->ws_rgba.release(); c->ws_list.release(); c->ws_rayd.release(); c->ws_raynf.release();
+  c->ws_contrib.release(); c->ws_zfine.release(); c->ws_out.release(); c->ws_in.release();
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  delete c;
+}
+
+extern "C" const char* kpn_last_error(const kpn_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+static void expected_dims(int n_kpt, int sp_level, int dims[NLAYER][2]) {
+  const int enc = (1 + 2 * sp_level) * n_kpt;
+  const int t[NLAYER][2] = {{128, enc + 64}, {128, 128}, {120, 136}, {64, 120}, {64, 128}, {64, 64}, {2, 64}, {24, 128},
+                            {16, 4}, {35, 16}, {64, 105}, {32, 64}, {32, 32}, {33, 32}, {32, 32}, {1, 32},
+                            {16, 37}, {8, 16}, {1, 8}};
+  memcpy(dims, t, sizeof(t));
+}
+
+extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
+  if (!c || !w) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  if (w->n_kpt < 1 || w->n_kpt > simt_max_kpt() || w->n_kpt > KPN_MAX_KPT)
+    KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "n_kpt=%d unsupported (1..%d)", w->n_kpt, simt_max_kpt());
+  if (w->sp_level < 0 || w->sp_level > MAX_SPL || (1 + 2 * w->sp_level) * w->n_kpt + 64 > 232)
+    KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "sp_level=%d unsupported", w->sp_level);
+  int dims[NLAYER][2];
+  expected_dims(w->n_kpt, w->sp_level, dims);
+  size_t total = 0;
+  DevWeightsF32 hw;
+  std::vector<size_t> woff(NLAYER), boff(NLAYER);
+  for (int l = 0; l < NLAYER; ++l) {
+    const kpn_layer& L = w->layer[l];
+    if (!L.w || !L.bias) KPN_FAIL(c, KPN_ERR_ARG, "layer %d: null weight/bias", l);
+    if (L.n_out != dims[l][0] || L.n_in != dims[l][1])
+      KPN_FAIL(c, KPN_ERR_ARG, "layer %d: shape (%d,%d) != expected (%d,%d)", l, L.n_out, L.n_in, dims[l][0], dims[l][1]);
+    hw.K[l] = L.n_in; hw.N[l] = L.n_out; hw.ldw[l] = (L.n_out + 31) / 32 * 32;
+    woff[l] = total; total += (size_t)hw.K[l] * hw.ldw[l];
+    boff[l] = total; total += (size_t)hw.ldw[l];
+  }
+  std::vector<float> host(total, 0.0f);
+  for (int l = 0; l < NLAYER; ++l) {
+    const kpn_layer& L = w->layer[l];
+    for (int o = 0; o < L.n_out; ++o) {
+      double scale = 1.0;
+      if (L.g) {  // weight norm, dim=0: w = g * v / ||v||_row  (reference src/utils.py:542-543)
+        double nn = 0.0;
+        for (int i = 0; i < L.n_in; ++i) nn += (double)L.w[(size_t)o * L.n_in + i] * (double)L.w[(size_t)o * L.n_in + i];
+        scale = (double)L.g[o] / std::sqrt(nn);
+      }
+      for (int i = 0; i < L.n_in; ++i)
+        host[woff[l] + (size_t)i * hw.ldw[l] + o] = (float)(scale * (double)L.w[(size_t)o * L.n_in + i]);
+      host[boff[l] + o] = L.bias[o];
+    }
+  }
+  KPN_CUDA(c, cudaDeviceSynchronize());  // the old buffer may still be in use
+  KPN_CUDA(c, c->wbuf.reserve(total * sizeof(float)));
+  KPN_CUDA(c, cudaMemcpy(c->wbuf.p, host.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  for (int l = 0; l < NLAYER; ++l) {
+    hw.wt[l] = c->wbuf.as<float>() + woff[l];
+    hw.bias[l] = c->wbuf.as<float>() + boff[l];
+  }
+  hw.ani_al_abs = std::fabs(w->ani_al);
+  KPN_CUDA(c, cudaMemcpy(c->d_wf32, &hw, sizeof(hw), cudaMemcpyHostToDevice));
+  c->n_kpt = w->n_kpt; c->sp_level = w->sp_level; c->sp_scale = w->sp_scale; c->sp_sigma = w->sp_sigma;
+  c->have_weights = true;
+  return KPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene
+// ---------------------------------------------------------------------------------------------
+static cudaMemcpyKind in_kind(int mem) { return mem == KPN_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice; }
+
+extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
+  if (!c || !s) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!c->have_weights) KPN_FAIL(c, KPN_ERR_STATE, "kpn_set_weights must precede kpn_set_scene");
+  if (s->n_views < 1 || s->n_views > 3) KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "n_views=%d unsupported (1..3)", s->n_views);
+  if (s->n_kpt != c->n_kpt) KPN_FAIL(c, KPN_ERR_ARG, "scene n_kpt=%d != weights n_kpt=%d", s->n_kpt, c->n_kpt);
+  if (!s->KRT || !s->extrin || !s->kpt3d || !s->bounds || !s->feat64 || !s->feat8 || !s->feat_tex || !s->img)
+    KPN_FAIL(c, KPN_ERR_ARG, "null scene pointer");
+  if (s->f64_c != 64 || s->f8_c != 8 || s->ftex_c != 8)
+    KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "feature channels (%d,%d,%d) != (64,8,8)", s->f64_c, s->f8_c, s->ftex_c);
+  if (s->mem != KPN_MEM_HOST && s->mem != KPN_MEM_DEVICE) KPN_FAIL(c, KPN_ERR_ARG, "bad mem kind");
+  const int V = s->n_views;
+  cudaMemcpyKind kind = in_kind(s->mem);
+
+  DevScene h;
+  memset(&h, 0, sizeof(h));
+  h.V = V; h.K = s->n_kpt;
+  h.wm1 = s->src_width - 1.0f; h.hm1 = s->src_height - 1.0f;
+  h.znear = s->znear; h.zfar = s->zfar;
+  h.sdf_invalid = 0.1f / s->nml_scale;
+  h.use_fg = s->fg != nullptr;
+  h.sp_scale = c->sp_scale;
+  h.inv2sig2 = 1.0f / (2.0f * c->sp_sigma * c->sp_sigma);
+  h.sp_level = c->sp_level;
+  {
+    double val = 1.0;
+    for (int l = 0; l < c->sp_level; ++l) { h.freq[l] = (float)(3.14159265358979323846 * val); val *= 2.0; }
+  }
+  struct MapIn { const float* src; int C, H, W, Cp; } maps[4] = {
+      {s->feat64, s->f64_c, s->f64_h, s->f64_w, 64}, {s->feat8, s->f8_c, s->f8_h, s->f8_w, 8},
+      {s->feat_tex, s->ftex_c, s->ftex_h, s->ftex_w, 8}, {s->img, 3, s->img_h, s->img_w, 4}};
+  MapDesc* descs[4] = {&h.f64, &h.f8, &h.ftex, &h.img};
+  for (int m = 0; m < 4; ++m) {
+    const MapIn& M = maps[m];
+    if (M.H < 1 || M.W < 1) KPN_FAIL(c, KPN_ERR_ARG, "map %d has empty extent", m);
+    size_t in_bytes = (size_t)V * M.C * M.H * M.W * sizeof(float);
+    size_t out_bytes = (size_t)V * M.Cp * M.H * M.W * sizeof(float);
+    const float* dsrc = M.src;
+    if (s->mem == KPN_MEM_HOST) {
+      KPN_CUDA(c, c->stage[m].reserve(in_bytes));
+      KPN_CUDA(c, cudaMemcpyAsync(c->stage[m].p, M.src, in_bytes, cudaMemcpyHostToDevice, st));
+      dsrc = c->stage[m].as<float>();
+    }
+    KPN_CUDA(c, c->atlas[m].reserve(out_bytes));
+    KPN_CUDA(c, launch_pack_nhwc_f32(dsrc, c->atlas[m].as<float>(), V, M.C, M.H, M.W, M.Cp, st));
+    c->launches++;
+    descs[m]->ptr = c->atlas[m].p; descs[m]->C = M.Cp; descs[m]->H = M.H; descs[m]->W = M.W;
+  }
+  if (s->fg) {
+    size_t bytes = (size_t)V * s->fg_h * s->fg_w;
+    KPN_CUDA(c, c->atlas_fg.reserve(bytes));
+    KPN_CUDA(c, cudaMemcpyAsync(c->atlas_fg.p, s->fg, bytes, kind, st));
+    h.fg.ptr = c->atlas_fg.p; h.fg.C = 1; h.fg.H = s->fg_h; h.fg.W = s->fg_w;
+  }
+  KPN_CUDA(c, cudaMemcpyAsync(c->d_scene, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  KPN_CUDA(c, cudaMemcpyAsync(c->d_raw_scene->KRT, s->KRT, sizeof(float) * 16 * V, kind, st));
+  KPN_CUDA(c, cudaMemcpyAsync(c->d_raw_scene->extrin, s->extrin, sizeof(float) * 16 * V, kind, st));
+  KPN_CUDA(c, cudaMemcpyAsync(c->d_raw_scene->kpt3d, s->kpt3d, sizeof(float) * 3 * s->n_kpt, kind, st));
+  KPN_CUDA(c, cudaMemcpyAsync(c->d_raw_scene->bounds, s->bounds, sizeof(float) * 6, kind, st));
+  KPN_CUDA(c, launch_prep_scene(c->d_raw_scene, c->d_scene, st));
+  c->launches++;
+  c->have_scene = true;
+  return KPN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shading of a batch of samples with the selected engine
+// ---------------------------------------------------------------------------------------------
+static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_mode, int slot, float* out5,
+                       uint8_t* valid_out, int engine, cudaStream_t st) {
+  (void)engine;
+  KPN_CUDA(c, c->ws_list.reserve((size_t)n * sizeof(int)));
+  int* counter = c->d_counters + slot;
+  KPN_CUDA(c, launch_compact(c->d_scene, src, n, query_mode, c->ws_list.as<int>(), counter, out5, valid_out, st));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profiling) {
+    if (c->ev_used + 2 > c->ev_pool.size()) {
+      cudaEvent_t a, b;
+      KPN_CUDA(c, cudaEventCreate(&a));
+      KPN_CUDA(c, cudaEventCreate(&b));
+      c->ev_pool.push_back(a); c->ev_pool.push_back(b);
+    }
+    e0 = c->ev_pool[c->ev_used]; e1 = c->ev_pool[c->ev_used + 1];
+    c->ev_used += 2;
+    KPN_CUDA(c, cudaEventRecord(e0, st));
+  }
+  KPN_CUDA(c, launch_shade_simt(c->d_scene, c->d_wf32, src, c->ws_list.as<int>(), counter, n, query_mode, out5,
+                                c->num_sms, st));
+  if (c->profiling) KPN_CUDA(c, cudaEventRecord(e1, st));
+  c->launches += 2;
+  return KPN_OK;
+}
+
+static int begin_counters(kpn_ctx* c, cudaStream_t st) {
+  KPN_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(int) * MAX_CHUNKS, st));
+  c->counters_used = 0;
+  c->last_total = 0;
+  return KPN_OK;
+}
+
+extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, const kpn_out* out, void* stream) {
+  if (!c || !tg || !op || !out) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!c->have_scene) KPN_FAIL(c, KPN_ERR_STATE, "kpn_set_scene must precede kpn_render");
+  const int Sc = op->sample_per_ray_c, Sf = op->fine ? op->sample_per_ray_f : 0;
+  if (Sc < 1 || Sc > max_coarse_samples()) KPN_FAIL(c, KPN_ERR_ARG, "sample_per_ray_c=%d out of range", Sc);
+  if (op->fine && (Sc < 3 || Sf < 1 || Sf > 1024)) KPN_FAIL(c, KPN_ERR_ARG, "fine pass needs S_c>=3 and 1<=S_f<=1024");
+  if (tg->nx < 1 || tg->ny < 1 || tg->step < 1) KPN_FAIL(c, KPN_ERR_ARG, "empty pixel lattice");
+  if (!tg->K || !tg->RT) KPN_FAIL(c, KPN_ERR_ARG, "null target camera");
+  const long long R = (long long)tg->nx * tg->ny;
+  const int Smax = Sc + Sf;
+  if (R * Smax >= (1ll << 40)) KPN_FAIL(c, KPN_ERR_ARG, "too many samples");
+
+  // target camera -> device constants
+  cudaMemcpyKind kind = in_kind(tg->mem);
+  KPN_CUDA(c, cudaMemcpyAsync(c->d_raw_target->K, tg->K, sizeof(float) * 16, kind, st));
+  KPN_CUDA(c, cudaMemcpyAsync(c->d_raw_target->RT, tg->RT, sizeof(float) * 16, kind, st));
+  DevTarget ht;
+  memset(&ht, 0, sizeof(ht));
+  ht.znear = tg->znear; ht.zfar = tg->zfar; ht.x0 = tg->x0; ht.y0 = tg->y0; ht.step = tg->step; ht.nx = tg->nx; ht.ny = tg->ny;
+  KPN_CUDA(c, cudaMemcpyAsync(c->d_target, &ht, sizeof(ht), cudaMemcpyHostToDevice, st));
+  KPN_CUDA(c, launch_prep_target(c->d_raw_target, c->d_target, st));
+  c->launches++;
+  const float* d_o = reinterpret_cast<const float*>(reinterpret_cast<const char*>(c->d_target) + offsetof(DevTarget, o));
+
+  // outputs: render into device planes, copy to the host at the end if requested
+  float* user[7] = {out->tex_fg, out->depth, out->alpha, out->tex_fg_fine, out->depth_fine, out->alpha_fine, out->sdf};
+  const int planes[7] = {3, 1, 1, 3, 1, 1, 1};
+  float* dev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const bool host_out = out->mem == KPN_MEM_HOST;
+  if (host_out) {
+    size_t tot = 0;
+    for (int i = 0; i < 7; ++i) if (user[i]) tot += (size_t)planes[i] * R;
+    KPN_CUDA(c, c->ws_out.reserve(tot * sizeof(float)));
+    size_t off = 0;
+    for (int i = 0; i < 7; ++i) if (user[i]) { dev[i] = c->ws_out.as<float>() + off; off += (size_t)planes[i] * R; }
+  } else {
+    for (int i = 0; i < 7; ++i) dev[i] = user[i];
+  }
+
+  long long Rc = (4ll << 20) / Smax;
+  Rc = (Rc / 128) * 128;
+  if (Rc < 128) Rc = 128;
+  if (Rc > R) Rc = R;
+  const long long nchunks = (R + Rc - 1) / Rc;
+  if (nchunks * 2 > MAX_CHUNKS) KPN_FAIL(c, KPN_ERR_ARG, "frame too large for one call (%lld chunks)", nchunks);
+  KPN_CUDA(c, c->ws_rayd.reserve((size_t)Rc * 3 * sizeof(float)));
+  KPN_CUDA(c, c->ws_raynf.reserve((size_t)Rc * 2 * sizeof(float)));
+  KPN_CUDA(c, c->ws_z.reserve((size_t)Rc * Sc * sizeof(float)));
+  KPN_CUDA(c, c->ws_rgba.reserve((size_t)Rc * Smax * 5 * sizeof(float)));
+  const bool need_contrib = op->fine || out->contrib;
+  if (need_contrib) KPN_CUDA(c, c->ws_contrib.reserve((size_t)Rc * Sc * sizeof(float)));
+  if (op->fine) KPN_CUDA(c, c->ws_zfine.reserve((size_t)Rc * Smax * sizeof(float)));
+  int rc = begin_counters(c, st);
+  if (rc != KPN_OK) return rc;
+  cudaMemcpyKind okind = host_out ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+
+  for (long long ch = 0; ch < nchunks; ++ch) {
+    const long long r0 = ch * Rc;
+    const int nr = (int)((R - r0) < Rc ? (R - r0) : Rc);
+    KPN_CUDA(c, launch_rays(c->d_scene, c->d_target, (int)r0, nr, c->ws_rayd.as<float>(), c->ws_raynf.as<float>(), st));
+    KPN_CUDA(c, launch_coarse_z(c->ws_raynf.as<float>(), nr, Sc, c->ws_z.as<float>(), st));
+    c->launches += 2;
+    SampleSrc src;
+    memset(&src, 0, sizeof(src));
+    src.mode = 0; src.S = Sc; src.ray_d = c->ws_rayd.as<float>(); src.z = c->ws_z.as<float>(); src.o = d_o;
+    rc = shade_batch(c, src, (long long)nr * Sc, 0, (int)(2 * ch), c->ws_rgba.as<float>(), nullptr, op->engine, st);
+    if (rc != KPN_OK) return rc;
+    c->last_total += (unsigned long long)nr * Sc;
+    KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), c->ws_z.as<float>(), (int)r0, nr, Sc, R, dev[0], dev[1], dev[2],
+                                 nullptr, need_contrib ? c->ws_contrib.as<float>() : nullptr, st));
+    c->launches++;
+    if (out->contrib)
+      KPN_CUDA(c, cudaMemcpyAsync(out->contrib + r0 * Sc, c->ws_contrib.p, (size_t)nr * Sc * sizeof(float), okind, st));
+    if (op->fine) {
+      if (op->z_fine_override) {
+        KPN_CUDA(c, cudaMemcpyAsync(c->ws_zfine.p, op->z_fine_override + r0 * Smax, (size_t)nr * Smax * sizeof(float),
+                                    in_kind(out->mem), st));
+      } else {
+        KPN_CUDA(c, launch_importance(c->ws_contrib.as<float>(), c->ws_z.as<float>(), nr, Sc, Sf, c->ws_zfine.as<float>(), st));
+        c->launches++;
+      }
+      src.S = Smax; src.z = c->ws_zfine.as<float>();
+      rc = shade_batch(c, src, (long long)nr * Smax, 0, (int)(2 * ch + 1), c->ws_rgba.as<float>(), nullptr, op->engine, st);
+      if (rc != KPN_OK) return rc;
+      c->last_total += (unsigned long long)nr * Smax;
+      KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), c->ws_zfine.as<float>(), (int)r0, nr, Smax, R, dev[3], dev[4],
+                                   dev[5], dev[6], nullptr, st));
+      c->launches++;
+      if (out->z_fine)
+        KPN_CUDA(c, cudaMemcpyAsync(out->z_fine + r0 * Smax, c->ws_zfine.p, (size_t)nr * Smax * sizeof(float), okind, st));
+    }
+  }
+  c->counters_used = (int)(2 * nchunks);
+  if (host_out) {
+    for (int i = 0; i < 7; ++i)
+      if (user[i]) KPN_CUDA(c, cudaMemcpyAsync(user[i], dev[i], (size_t)planes[i] * R * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  return KPN_OK;
+}
+
+extern "C" int kpn_query(kpn_ctx* c, const float* pts, const float* view, int n, float* out5, uint8_t* valid, int mem,
+                         const kpn_opts* op, void* stream) {
+  if (!c || !pts || !view || !out5 || n < 0) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!c->have_scene) KPN_FAIL(c, KPN_ERR_STATE, "kpn_set_scene must precede kpn_query");
+  int rc = begin_counters(c, st);
+  if (rc != KPN_OK) return rc;
+  if (n == 0) return KPN_OK;
+  const float* dp = pts; const float* dv = view;
+  float* dout = out5; uint8_t* dvalid = valid;
+  if (mem == KPN_MEM_HOST) {
+    size_t fb = (size_t)n * 3 * sizeof(float);
+    KPN_CUDA(c, c->ws_in.reserve(2 * fb));
+    KPN_CUDA(c, cudaMemcpyAsync(c->ws_in.p, pts, fb, cudaMemcpyHostToDevice, st));
+    KPN_CUDA(c, cudaMemcpyAsync(c->ws_in.as<char>() + fb, view, fb, cudaMemcpyHostToDevice, st));
+    dp = c->ws_in.as<float>(); dv = reinterpret_cast<const float*>(c->ws_in.as<char>() + fb);
+    KPN_CUDA(c, c->ws_out.reserve((size_t)n * 5 * sizeof(float) + (size_t)n));
+    dout = c->ws_out.as<float>();
+    dvalid = reinterpret_cast<uint8_t*>(c->ws_out.as<char>() + (size_t)n * 5 * sizeof(float));
+  } else if (!dvalid) {
+    KPN_CUDA(c, c->ws_out.reserve((size_t)n));
+    dvalid = c->ws_out.as<uint8_t>();
+  }
+  const long long chunk = 4ll << 20;
+  const long long nchunks = (n + chunk - 1) / chunk;
+  if (nchunks > MAX_CHUNKS) KPN_FAIL(c, KPN_ERR_ARG, "too many points");
+  for (long long ch = 0; ch < nchunks; ++ch) {
+    long long off = ch * chunk;
+    long long m = (n - off) < chunk ? (n - off) : chunk;
+    SampleSrc src;
+    memset(&src, 0, sizeof(src));
+    src.mode = 1; src.pts = dp + 3 * off; src.view = dv + 3 * off;
+    rc = shade_batch(c, src, m, 1, (int)ch, dout + 5 * off, dvalid + off, op ? op->engine : 0, st);
+    if (rc != KPN_OK) return rc;
+  }
+  c->counters_used = (int)nchunks;
+  c->last_total = (unsigned long long)n;
+  if (mem == KPN_MEM_HOST) {
+    KPN_CUDA(c, cudaMemcpyAsync(out5, dout, (size_t)n * 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (valid) KPN_CUDA(c, cudaMemcpyAsync(valid, dvalid, (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  return KPN_OK;
+}
+
+extern "C" int kpn_get_stats(kpn_ctx* c, kpn_stats* stats, void* stream) {
+  if (!c || !stats) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int> h(c->counters_used > 0 ? c->counters_used : 1, 0);
+  if (c->counters_used > 0)
+    KPN_CUDA(c, cudaMemcpyAsync(h.data(), c->d_counters, sizeof(int) * c->counters_used, cudaMemcpyDeviceToHost, st));
+  KPN_CUDA(c, cudaStreamSynchronize(st));
+  unsigned long long valid = 0;
+  for (int i = 0; i < c->counters_used; ++i) valid += (unsigned long long)h[i];
+  stats->samples_total = c->last_total;
+  stats->samples_valid = valid;
+  stats->kernel_launches = c->launches;
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    float t = 0.0f;
+    KPN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[i], c->ev_pool[i + 1]));
+    ms += (double)t;
+  }
+  stats->shade_launches = c->ev_used / 2;
+  stats->shade_ms = ms;
+  c->ev_used = 0;
+  return KPN_OK;
+}
+
+extern "C" int kpn_set_profiling(kpn_ctx* c, int enable) {
+  if (!c) return KPN_ERR_ARG;
+  c->profiling = enable != 0;
+  return KPN_OK;
+}

@@ -1,0 +1,79 @@
+"""Multi-GPU partitioning of the ray-march path: one process per GPU, scene replicated, rays sharded.
+
+The reference has no multi-GPU rendering; rays are independent, so the only
+exchange step is ONE all-gather of the rendered shards (NCCL over NVLink on the GPU box, gloo in
+the CPU tests).  Two partitions:
+  * ``row_shard`` / ``gather_rows``: one frame split into contiguous row bands (BASELINE config 4);
+  * ``gather_views``: one novel view per rank (BASELINE config 5, render_dynamic.py-style sweep).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise torch.distributed from torchrun's environment.  Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def row_shard(height: int, rank: int, world: int):
+    """Contiguous row band [y0, y0+ny) of rank ``rank``; heights that do not divide evenly give the
+    first ``height % world`` ranks one extra row."""
+    base, rem = divmod(height, world)
+    ny = base + (1 if rank < rem else 0)
+    y0 = rank * base + min(rank, rem)
+    return y0, ny
+
+
+def _all_gather_stack(t: torch.Tensor, world: int) -> torch.Tensor:
+    """One all-gather; returns (world, *t.shape).  The output is laid out as a dim-0 concatenation,
+    which both NCCL and gloo accept for ``all_gather_into_tensor``."""
+    t = t.contiguous()
+    if t.dim() == 0:
+        t = t.reshape(1)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    return out.view(world, *t.shape)
+
+
+def gather_rows(shard: torch.Tensor, height: int, rank: int, world: int) -> torch.Tensor:
+    """All-gather row bands of a planar image (..., ny, W) into (..., height, W) on every rank."""
+    if world == 1:
+        return shard
+    base, rem = divmod(height, world)
+    if rem == 0:
+        out = _all_gather_stack(shard, world)
+        # (world, ..., ny, W) -> (..., world*ny, W)
+        nd = shard.dim()
+        perm = list(range(1, nd - 1)) + [0, nd - 1, nd]
+        return out.permute(*perm).reshape(*shard.shape[:-2], height, shard.shape[-1])
+    # ragged bands: pad to the tallest band, gather, then trim
+    ny_max = base + 1
+    pad = torch.zeros(*shard.shape[:-2], ny_max, shard.shape[-1], dtype=shard.dtype, device=shard.device)
+    pad[..., : shard.shape[-2], :] = shard
+    out = _all_gather_stack(pad, world)
+    bands = [out[r][..., : row_shard(height, r, world)[1], :] for r in range(world)]
+    return torch.cat(bands, dim=-2)
+
+
+def gather_views(frame: torch.Tensor, world: int) -> torch.Tensor:
+    """All-gather one rendered frame per rank into (world, ...) on every rank."""
+    if world == 1:
+        return frame[None]
+    return _all_gather_stack(frame, world)

@@ -1,0 +1,316 @@
+"""Drop-in ``KeypointNeRF`` for the reference's volumetric-rendering hot path.
+
+Mirrors the Python surface the reference's Lightning module calls:
+``KeypointNeRF(cfg)`` with the same sub-module names / ``state_dict`` keys for the
+hot-path networks (reference ``src/model.py:559-609``), ``query`` (690), and the static
+``render_pifu_nerf`` (897) / ``batch_render_pifu_nerf`` (942) entry points with the same
+positional order and ``**config`` keys.  All per-sample arithmetic runs in the CUDA
+library behind ``include/kpnerf_b200.h``; this file only marshals tensors.
+
+Out of scope here: the 2-D image encoders (``geo_encoder``,
+``tex_encoder``) and the training ``forward``.  Encoders can be attached by assigning
+modules to ``net.geo_encoder`` / ``net.tex_encoder``; otherwise pass the feature maps
+explicitly, as the reference's tile entry already allows (``feat_geo``, ``feat_tex``).
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn as nn
+
+from .renderer import RayMarcher
+
+
+class _WNLinear(nn.Module):
+    """Parameter holder with the keys of ``weight_norm(nn.Linear)`` (reference ``src/utils.py:542-543``):
+    ``linear.bias``, ``linear.weight_g`` (out,1), ``linear.weight_v`` (out,in)."""
+
+    class _P(nn.Module):
+        def __init__(self, n_in, n_out, wn):
+            super().__init__()
+            self.bias = nn.Parameter(torch.zeros(n_out))
+            if wn:
+                v = torch.empty(n_out, n_in)
+                nn.init.kaiming_uniform_(v, a=5 ** 0.5)
+                self.weight_g = nn.Parameter(v.norm(dim=1, keepdim=True))
+                self.weight_v = nn.Parameter(v)
+            else:
+                w = torch.empty(n_out, n_in)
+                nn.init.kaiming_normal_(w, a=0, mode="fan_in", nonlinearity="relu")
+                self.weight = nn.Parameter(w)
+
+    def __init__(self, n_in, n_out, wn):
+        super().__init__()
+        self.linear = self._P(n_in, n_out, wn)
+
+
+class _LayerStack(nn.Module):
+    def __init__(self, dims_in, dims_out):
+        super().__init__()
+        n = len(dims_out)
+        self.layers = nn.ModuleList([_WNLinear(i, o, wn=(k != n - 1)) for k, (i, o) in enumerate(zip(dims_in, dims_out))])
+
+
+class MLPUNetFusion(nn.Module):
+    """Parameters of the geometry MLP (reference ``src/utils.py:476-517``): ``layers1`` (per-view
+    MLP-UNet with feature skips) and ``layers2`` (density head after view pooling)."""
+
+    def __init__(self, n_dims1, n_dims2, skip_dims, skip_layers, nl_layer="softplus", norm="weight",
+                 pool_types=("mean", "var"), **kwargs):
+        super().__init__()
+        if nl_layer != "softplus" or norm != "weight" or list(pool_types) != ["mean", "var"]:
+            raise NotImplementedError("only the configs/zju.json geometry MLP (softplus, weight norm, mean+var) is built")
+        skip = {j: skip_dims[i] for i, j in enumerate(skip_layers)}
+        d_in = [n_dims1[i] + skip.get(i, 0) for i in range(len(n_dims1) - 1)]
+        self.pool = nn.Module()
+        self.layers1 = _LayerStack(d_in, n_dims1[1:])
+        self.layers2 = _LayerStack(n_dims2[:-1], n_dims2[1:])
+
+
+class IBRRenderingHead(nn.Module):
+    """Parameters of the colour-blending head (reference ``src/model.py:1239-1258``)."""
+
+    def __init__(self, in_channels=32, **kwargs):
+        super().__init__()
+        c = in_channels + 3
+        self.ani_al = nn.Parameter(torch.tensor(0.2))
+        seq = lambda *dims: nn.Sequential(*[m for i in range(len(dims) - 1)
+                                            for m in (nn.Linear(dims[i], dims[i + 1]), nn.ELU(inplace=True))])
+        self.ray_encoder = seq(4, 16, c)
+        self.base_layer = seq(c * 3, 64, 32)
+        self.vis_layer1 = seq(32, 32, 33)
+        self.vis_layer2 = nn.Sequential(nn.Linear(32, 32), nn.ELU(inplace=True), nn.Linear(32, 1), nn.Sigmoid())
+        self.out_layer = nn.Sequential(nn.Linear(37, 16), nn.ELU(inplace=True), nn.Linear(16, 8), nn.ELU(inplace=True),
+                                       nn.Linear(8, 1))
+
+
+class SpatialEncoder(nn.Module):
+    """Hyper-parameters of the relative keypoint encoding (reference ``src/spatial.py:9-21``)."""
+
+    def __init__(self, sp_level, sp_type, scale, n_kpt, **kwargs):
+        super().__init__()
+        if sp_type != "rel_z_decay":
+            raise NotImplementedError(f"sp_type={sp_type!r}: only 'rel_z_decay' (configs/zju.json:41) is built")
+        self.sp_type, self.sp_level, self.n_kpt, self.scale = sp_type, sp_level, n_kpt, scale
+        self.kwargs = kwargs
+        self.register_buffer("center", torch.tensor(kwargs.get("center", [0.0, 0.0, 0.0])).float())
+
+    def get_dim(self):
+        return (1 + 2 * self.sp_level) * self.n_kpt
+
+
+_HOT_PREFIXES = ("mlp_geo.", "mlp_tex.", "ibr_compress_gfeat.")
+
+
+class KeypointNeRF(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        model_cfg = cfg["models"]["KeypointNeRF"]
+        self.train_out_h = model_cfg.get("train_out_h", 64)
+        self.train_out_w = model_cfg.get("train_out_w", 64)
+        self.disable_fg_mask = model_cfg.get("disable_fg_mask", False)
+        self.sp_encoder = SpatialEncoder(**model_cfg["sp_args"])
+        geo_args = copy.deepcopy(model_cfg["mlp_geo_args"])
+        geo_args["n_dims1"][0] = self.sp_encoder.get_dim()
+        self.mlp_geo = MLPUNetFusion(**geo_args)
+        self.mlp_tex = IBRRenderingHead(**model_cfg["mlp_tex_args"]["args"])
+        self.ibr_compress_gfeat = nn.Linear(model_cfg["mlp_tex_args"]["gcompress"]["in_ch"],
+                                            model_cfg["mlp_tex_args"]["gcompress"]["out_ch"])
+        self.geo_encoder = None   # attach HGFilterV2-compatible module to use attach_geo_feat
+        self.tex_encoder = None   # attach ResBlkEncoder-compatible module to use attach_tex_feat
+        self.sp_encoder_postfusion = None
+        self.ds_geo = model_cfg.get("ds_geo", 0)
+        self.ds_tex = model_cfg.get("ds_tex", 0)
+        self.v_level = model_cfg.get("v_level", 0)
+        self.dr_level = model_cfg.get("dr_level", 5)
+        self.feat_geo = None
+        self.feat_tex = None
+        self.kwargs = model_cfg
+        self.vgg_loss = None
+        self.disable_bg = True
+        self._marcher = None
+        self._w_key = None
+        self._scene_key = None
+        self.engine = 0
+
+    # ---- feature caching (reference src/model.py:642-688) -----------------------------------------
+    def attach_im_feat(self, im, return_val=False):
+        if return_val:
+            out = {"feat_geo": self.attach_geo_feat(im, True)}
+            ft = self.attach_tex_feat(im, True)
+            if ft is not None:
+                out["feat_tex"] = ft
+            return out
+        self.attach_geo_feat(im)
+        self.attach_tex_feat(im)
+
+    def attach_geo_feat(self, im, return_val=False):
+        if self.geo_encoder is None:
+            raise RuntimeError("no geo_encoder attached: pass feat_geo explicitly (image encoders are outside the "
+                               "ray-march hot path, SURVEY.md section 8f)")
+        if not return_val:
+            self.im = im.clone()
+        if im.dim() == 5:
+            im = im.view(-1, *im.shape[2:])
+        for _ in range(self.ds_geo):
+            im = torch.nn.functional.avg_pool2d(im, 2, stride=2)
+        self.feat_geo = self.geo_encoder(2.0 * im - 1.0)
+        if return_val:
+            return self.feat_geo
+
+    def attach_tex_feat(self, im, return_val=False):
+        if self.tex_encoder is None:
+            return None
+        if im.dim() == 5:
+            im = im.view(-1, *im.shape[2:])
+        for _ in range(self.ds_tex):
+            im = torch.nn.functional.avg_pool2d(im, 2, stride=2)
+        self.feat_tex = self.tex_encoder(2.0 * im - 1.0)
+        if return_val:
+            return self.feat_tex
+
+    def detach_im_feat(self):
+        self.feat_geo = None
+        self.feat_tex = None
+
+    # ---- marshalling -----------------------------------------------------------------------------
+    def _device_index(self):
+        p = self.ibr_compress_gfeat.weight
+        if not p.is_cuda:
+            raise RuntimeError("KeypointNeRF must live on a CUDA device (.cuda()): the ray-march path has no CPU fallback")
+        return p.device.index if p.device.index is not None else torch.cuda.current_device()
+
+    def marcher(self) -> RayMarcher:
+        dev = self._device_index()
+        if self._marcher is None or self._marcher.device != dev:
+            self._marcher = RayMarcher(dev)
+            self._w_key = None
+            self._scene_key = None
+        hot = {k: v for k, v in self.state_dict().items() if k.startswith(_HOT_PREFIXES)}
+        key = tuple((k, v.data_ptr(), v._version) for k, v in hot.items())
+        if key != self._w_key:
+            sp = self.sp_encoder
+            self._marcher.set_weights(hot, n_kpt=sp.n_kpt, sp_level=sp.sp_level, sp_scale=sp.scale,
+                                      sp_sigma=sp.kwargs.get("sigma", 150.0))
+            self._w_key = key
+            self._scene_key = None
+        return self._marcher
+
+    def marcher_dtype(self) -> str:
+        """Arithmetic type of the dense layers in the selected engine."""
+        return "fp32"
+
+    def _bind_scene(self, cam, feat_geo, feat_tex, sp_data, img, fg_mask, bounds):
+        m = self.marcher()
+        tensors = [cam["KRT"], sp_data["extrin"], sp_data["kpt3d"], bounds, feat_geo[0], feat_geo[1], feat_tex, img]
+        if fg_mask is not None:
+            tensors.append(fg_mask)
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors) + (
+            float(cam["width"]), float(cam["height"]), float(cam["znear"]), float(cam["zfar"]))
+        if key != self._scene_key:
+            m.set_scene(KRT=cam["KRT"], extrin=sp_data["extrin"], kpt3d=sp_data["kpt3d"].reshape(-1, 3), bounds=bounds,
+                        feat64=feat_geo[0], feat8=feat_geo[1], feat_tex=feat_tex, img=img,
+                        fg=None if self.disable_fg_mask else fg_mask,
+                        width=cam["width"], height=cam["height"], znear=cam["znear"], zfar=cam["zfar"],
+                        nml_scale=cam.get("nml_scale", 100.0))
+            self._scene_key = key
+        return m
+
+    # ---- query (reference src/model.py:690-782) --------------------------------------------------
+    def query(self, pts, cam, feat_geo=None, feat_tex=None, n_views=1, sp_data={}, tx_data={}, view=None,
+              n_pts_samples=-1, **kwargs):
+        """Returns ``(out (B,N,5) = [sdf_raw, rad, r, g, b], valid (B,N,1) bool)``; B must be 1."""
+        assert pts.shape[0] == 1, "batch size 1 only (the reference's bbox test already requires it, src/model.py:1191)"
+        feat_geo = self.feat_geo if feat_geo is None else feat_geo
+        feat_tex = self.feat_tex if feat_tex is None else feat_tex
+        m = self._bind_scene(cam, feat_geo, feat_tex, sp_data, tx_data["img"], kwargs.get("src_foreground_mask"),
+                             kwargs.get("bounds", torch.zeros(1, 2, 3)))
+        out, valid = m.query(pts[0], view[0], engine=self.engine)
+        return out[None], valid[None, :, None]
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("the training forward (autograd through the ray-march) is outside this build's "
+                                  "scope (SURVEY.md section 8f.3); use the reference implementation to train")
+
+    # ---- full frame (reference src/model.py:897-940) ---------------------------------------------
+    @staticmethod
+    def render_pifu_nerf(net, img_in, cam_in, cam_tar, level=5, sp_data={}, bkg_emb=None, camcenter=None,
+                         objcenter=None, tar_img=None, **config):
+        """Same contract as the reference: dict of detached CPU tensors ``(C,H,W)``.  The reference
+        renders stride^2 strided 64x64-style passes and pixel-shuffles them; rays are independent, so
+        this renders the frame in ONE launch sequence with no per-pass host synchronisation."""
+        config = dict(config)
+        feat_geo = config.pop("feat_geo", None)
+        feat_tex = config.pop("feat_tex", None)
+        if feat_geo is None:
+            feat_geo = net.attach_geo_feat(img_in, return_val=True)
+        if feat_tex is None:
+            feat_tex = net.attach_tex_feat(img_in, return_val=True)
+        out = KeypointNeRF._render(net, img_in, cam_in, cam_tar, 1, 0, 0, tar_img, feat_geo, feat_tex, sp_data,
+                                   out_device="cpu", **config)
+        ret = {}
+        for k, v in out.items():
+            if v is None or v.dim() < 3:
+                continue
+            ret[k] = v[0] if v.dim() == 4 else v  # (B,C,h,w) -> (C,h,w); (B,h,w) -> (1,h,w) like the reference
+        return ret
+
+    # ---- one pass (reference src/model.py:942-1108) ----------------------------------------------
+    @staticmethod
+    def batch_render_pifu_nerf(net, img_in, cam_in, n_views, cam_tar, level=2, stride=0, tar_img=None, feat_geo=None,
+                               feat_tex=None, sp_data={}, objcenter=None, **config):
+        if net.training:
+            raise NotImplementedError("training branch (random patch, jitter, view dropout) is outside this build's scope")
+        assert img_in.shape[0] // n_views == 1, "batch size 1 only"
+        if feat_geo is None:
+            feat_geo = net.attach_geo_feat(img_in, return_val=True)
+        if feat_tex is None:
+            feat_tex = net.attach_tex_feat(img_in, return_val=True)
+        step = 2 ** (level - 1)
+        if isinstance(stride, int):
+            assert stride < step
+            x_off = y_off = stride
+        elif isinstance(stride, torch.Tensor):
+            sv = stride.reshape(-1).tolist()
+            assert max(sv) < step
+            x_off, y_off = int(sv[0]), int(sv[1])
+        else:
+            raise NotImplementedError("unsupported stride type")
+        return KeypointNeRF._render(net, img_in, cam_in, cam_tar, step, x_off, y_off, tar_img, feat_geo, feat_tex,
+                                    sp_data, out_device=None, **config)
+
+    @staticmethod
+    def _render(net, img_in, cam_in, cam_tar, step, x_off, y_off, tar_img, feat_geo, feat_tex, sp_data, out_device,
+                **config):
+        S_c = config.get("sample_per_ray_c", 64)
+        S_f = config.get("sample_per_ray_f", 64)
+        fine = config.get("fine", False)
+        if not config.get("uniform", False):
+            raise NotImplementedError("uniform=False (stratified jitter) is a training-time option outside this build")
+        if config.get("separate_cf", False) or config.get("rand_noise_std", 0.0) > 0.0 and net.training:
+            raise NotImplementedError("separate_cf / density noise are training-time options outside this build")
+        width = int(cam_tar.get("width", cam_in["width"]))
+        height = int(cam_tar.get("height", cam_in["height"]))
+        znear = cam_tar.get("znear", cam_in["znear"])
+        zfar = cam_tar.get("zfar", cam_in["zfar"])
+        assert width % step == 0 and height % step == 0
+        nx, ny = width // step, height // step
+        m = net._bind_scene(cam_in, feat_geo, feat_tex, sp_data, img_in, config.get("src_foreground_mask"), config["bounds"])
+        res = m.render(K=cam_tar["K"], RT=cam_tar["RT"], znear=znear, zfar=zfar, x0=x_off, y0=y_off, step=step,
+                       nx=nx, ny=ny, S_c=S_c, S_f=S_f, fine=fine, out_device=out_device, engine=net.engine,
+                       ert_eps=config.get("ert_eps", 0.0))
+        out = {"tex_fg": res["tex_fg"][None], "depth": res["depth"][None], "alpha": res["alpha"][None]}
+        if fine:
+            out.update({"tex_fg_fine": res["tex_fg_fine"][None], "depth_fine": res["depth_fine"][None],
+                        "alpha_fine": res["alpha_fine"][None], "sdf": res["sdf"][None]})
+        if tar_img is not None:  # reference src/model.py:1097-1107
+            with torch.no_grad():
+                ys = torch.arange(y_off, height, step, device=tar_img.device)
+                xs = torch.arange(x_off, width, step, device=tar_img.device)
+                sub = tar_img[:, :, ys][:, :, :, xs]
+                out["tar_img"] = sub.to(out["tex_fg"].device)
+                if "msk" in config:
+                    msk = config["msk"].reshape(1, 1, height, width)
+                    out["tar_alpha"] = msk[:, :, ys][:, :, :, xs].float().to(out["tex_fg"].device)
+        return out
