@@ -108,7 +108,10 @@ typedef struct {
   int fine;               /* config["fine"] */
   float ert_eps;          /* early-ray-termination transmittance threshold; 0 = off (reference behaviour) */
   const float* z_fine_override; /* optional (R, S_c+S_f) sorted depths replacing the resampled ones (test hook; same kpn_mem as kpn_out) */
-  int engine;             /* 0 = default, 1 = fp32 SIMT reference engine (debug/parity anchor) */
+  int engine;             /* 0 = default: tcgen05, fp16 operands with two-term (hi+lo) weights, fp32 accumulate;
+                             1 = fp32 CUDA-core engine (parity anchor; also used for shapes the tensor-core engine
+                                 does not cover: n_views != 3, n_kpt not in {18,24}, sp_level != 3);
+                             2 = tcgen05 with single-term fp16 weights (faster issue, ~2x the rounding error) */
 } kpn_opts;
 
 /* Outputs of batch_render_pifu_nerf (reference src/model.py:1065-1096); any pointer may be NULL. */
@@ -165,6 +168,10 @@ int kpn_get_stats(kpn_ctx* ctx, kpn_stats* stats, void* stream);
 
 /* enable != 0: bracket every shading-kernel launch with CUDA events on its stream (no sync). */
 int kpn_set_profiling(kpn_ctx* ctx, int enable);
+
+/* Unit test hook for the tensor-core primitive (tests/test_gpu_umma.py): D(128,N) fp32 = A(128,K) fp16 * B(N,K)^T fp16
+ * on one CTA through tcgen05.mma.  Device pointers.  variant bit0: B core-matrix arrangement, bit1: A from shared memory. */
+int kpn_selftest_umma(int N, int K, const void* A, const void* B, float* D, int variant, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "kpn_launch.h"
+#include "kpn_tc.cuh"
 
 using namespace kpn;
 
@@ -55,6 +56,11 @@ struct kpn_ctx {
   DevTarget* d_target = nullptr;
   DevWeightsF32* d_wf32 = nullptr;
   DevBuf wbuf;
+  DevBuf wblob;                // fp16 weight tiles of the tensor-core engine (core-matrix layout)
+  DevBuf wlo;                  // fp16 rounding residuals of the geometry/density weight tiles (streamed from L2)
+  TcConsts tcc;                // fp32 constants of the tensor-core engine (kernel parameter)
+  bool tc_weights = false;
+  int scene_views = 0;
   int* d_counters = nullptr;   // [MAX_CHUNKS]
   int counters_used = 0;
   unsigned long long last_total = 0;
@@ -115,6 +121,8 @@ extern "C" void kpn_destroy(kpn_ctx* c) {
   cudaFree(c->d_raw_scene); cudaFree(c->d_scene); cudaFree(c->d_raw_target); cudaFree(c->d_target);
   cudaFree(c->d_wf32); cudaFree(c->d_counters);
   c->wbuf.release();
+  c->wblob.release();
+  c->wlo.release();
   for (auto& b : c->stage) b.release();
   for (auto& b : c->atlas) b.release();
   c->atlas_fg.release();
@@ -159,8 +167,10 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
     boff[l] = total; total += (size_t)hw.ldw[l];
   }
   std::vector<float> host(total, 0.0f);
+  std::vector<std::vector<float>> We(NLAYER);  // effective weights, row-major [n_out][n_in]
   for (int l = 0; l < NLAYER; ++l) {
     const kpn_layer& L = w->layer[l];
+    We[l].resize((size_t)L.n_out * L.n_in);
     for (int o = 0; o < L.n_out; ++o) {
       double scale = 1.0;
       if (L.g) {  // weight norm, dim=0: w = g * v / ||v||_row  (reference src/utils.py:542-543)
@@ -168,8 +178,11 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
         for (int i = 0; i < L.n_in; ++i) nn += (double)L.w[(size_t)o * L.n_in + i] * (double)L.w[(size_t)o * L.n_in + i];
         scale = (double)L.g[o] / std::sqrt(nn);
       }
-      for (int i = 0; i < L.n_in; ++i)
-        host[woff[l] + (size_t)i * hw.ldw[l] + o] = (float)(scale * (double)L.w[(size_t)o * L.n_in + i]);
+      for (int i = 0; i < L.n_in; ++i) {
+        float e = (float)(scale * (double)L.w[(size_t)o * L.n_in + i]);
+        We[l][(size_t)o * L.n_in + i] = e;
+        host[woff[l] + (size_t)i * hw.ldw[l] + o] = e;
+      }
       host[boff[l] + o] = L.bias[o];
     }
   }
@@ -182,6 +195,52 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
   }
   hw.ani_al_abs = std::fabs(w->ani_al);
   KPN_CUDA(c, cudaMemcpy(c->d_wf32, &hw, sizeof(hw), cudaMemcpyHostToDevice));
+  // ---- tensor-core engine: fp16 weight tiles in the interleaved core-matrix layout + fp32 constants
+  c->tc_weights = false;
+  if (tc_supported(3, w->n_kpt, w->sp_level)) {
+    const TcPlan plan = make_tc_plan(w->n_kpt);
+    std::vector<__half> blob(plan.total_bytes / 2, __float2half_rn(0.0f));
+    const size_t lo_bytes = tc_weight_lo_bytes(w->n_kpt);
+    std::vector<__half> blob_lo(lo_bytes / 2, __float2half_rn(0.0f));
+    // stage -> (layer, first row in the tile); stage 4 stacks the density layer 0 and the colour compress layer
+    const int stage_layer[TC_NSTAGE] = {L_GEO0, L_GEO1, L_GEO2, L_GEO3, L_DEN0, L_DEN1, L_BASE0, L_BASE1, L_VIS1A, L_VIS1B, L_VIS2A, L_OUT0};
+    auto put = [&](int stage, int layer, int row0) {
+      const kpn_layer& L = w->layer[layer];
+      const int Np = plan.st[stage].Np;
+      for (int o = 0; o < L.n_out; ++o)
+        for (int i = 0; i < L.n_in; ++i)
+        {
+          const size_t at = (plan.st[stage].off + tc::core_offset_bytes(row0 + o, i, Np)) / 2;
+          const float wv = We[layer][(size_t)o * L.n_in + i];
+          const __half hi = __float2half_rn(wv);
+          blob[at] = hi;
+          if (at < blob_lo.size()) blob_lo[at] = __float2half_rn(wv - __half2float(hi));
+        }
+    };
+    for (int sidx = 0; sidx < TC_NSTAGE; ++sidx) put(sidx, stage_layer[sidx], 0);
+    put(4, L_CMP, 64);
+    KPN_CUDA(c, c->wblob.reserve(plan.total_bytes));
+    KPN_CUDA(c, cudaMemcpy(c->wblob.p, blob.data(), plan.total_bytes, cudaMemcpyHostToDevice));
+    KPN_CUDA(c, c->wlo.reserve(lo_bytes));
+    KPN_CUDA(c, cudaMemcpy(c->wlo.p, blob_lo.data(), lo_bytes, cudaMemcpyHostToDevice));
+    TcConsts& T = c->tcc;
+    memset(&T, 0, sizeof(T));
+    auto bias = [&](int layer, float* dst) { for (int o = 0; o < w->layer[layer].n_out; ++o) dst[o] = w->layer[layer].bias[o]; };
+    bias(L_GEO0, T.b_l0); bias(L_GEO1, T.b_l1); bias(L_GEO2, T.b_l2); bias(L_GEO3, T.b_l3);
+    bias(L_DEN0, T.b_p0); bias(L_CMP, T.b_cmp); bias(L_DEN1, T.b_p1);
+    bias(L_BASE0, T.b_base0); bias(L_BASE1, T.b_base1); bias(L_VIS1A, T.b_vis1a); bias(L_VIS1B, T.b_vis1b);
+    bias(L_VIS2A, T.b_vis2a); bias(L_OUT0, T.b_out0);
+    for (int o = 0; o < 2; ++o) { for (int i = 0; i < 64; ++i) T.w_p2[o][i] = We[L_DEN2][o * 64 + i]; T.b_p2[o] = w->layer[L_DEN2].bias[o]; }
+    for (int o = 0; o < 16; ++o) { for (int i = 0; i < 4; ++i) T.w_re0[o][i] = We[L_RE0][o * 4 + i]; T.b_re0[o] = w->layer[L_RE0].bias[o]; }
+    for (int o = 0; o < 35; ++o) { for (int i = 0; i < 16; ++i) T.w_re1[o][i] = We[L_RE1][o * 16 + i]; T.b_re1[o] = w->layer[L_RE1].bias[o]; }
+    for (int i = 0; i < 32; ++i) T.w_vis2b[i] = We[L_VIS2B][i];
+    T.b_vis2b = w->layer[L_VIS2B].bias[0];
+    for (int o = 0; o < 8; ++o) { for (int i = 0; i < 16; ++i) T.w_out1[o][i] = We[L_OUT1][o * 16 + i]; T.b_out1[o] = w->layer[L_OUT1].bias[o]; }
+    for (int i = 0; i < 8; ++i) T.w_out2[i] = We[L_OUT2][i];
+    T.b_out2 = w->layer[L_OUT2].bias[0];
+    T.ani_abs = std::fabs(w->ani_al);
+    c->tc_weights = true;
+  }
   c->n_kpt = w->n_kpt; c->sp_level = w->sp_level; c->sp_scale = w->sp_scale; c->sp_sigma = w->sp_sigma;
   c->have_weights = true;
   return KPN_OK;
@@ -255,6 +314,7 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
   KPN_CUDA(c, launch_prep_scene(c->d_raw_scene, c->d_scene, st));
   c->launches++;
   c->have_scene = true;
+  c->scene_views = V;
   return KPN_OK;
 }
 
@@ -263,7 +323,7 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
 // ---------------------------------------------------------------------------------------------
 static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_mode, int slot, float* out5,
                        uint8_t* valid_out, int engine, cudaStream_t st) {
-  (void)engine;
+  const bool use_tc = engine != 1 && c->tc_weights && tc_supported(c->scene_views, c->n_kpt, c->sp_level);
   KPN_CUDA(c, c->ws_list.reserve((size_t)n * sizeof(int)));
   int* counter = c->d_counters + slot;
   KPN_CUDA(c, launch_compact(c->d_scene, src, n, query_mode, c->ws_list.as<int>(), counter, out5, valid_out, st));
@@ -279,8 +339,12 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_
     c->ev_used += 2;
     KPN_CUDA(c, cudaEventRecord(e0, st));
   }
-  KPN_CUDA(c, launch_shade_simt(c->d_scene, c->d_wf32, src, c->ws_list.as<int>(), counter, n, query_mode, out5,
-                                c->num_sms, st));
+  if (use_tc)
+    KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), engine == 2 ? nullptr : c->wlo.as<uint8_t>(), c->n_kpt,
+                                src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->num_sms, st));
+  else
+    KPN_CUDA(c, launch_shade_simt(c->d_scene, c->d_wf32, src, c->ws_list.as<int>(), counter, n, query_mode, out5,
+                                  c->num_sms, st));
   if (c->profiling) KPN_CUDA(c, cudaEventRecord(e1, st));
   c->launches += 2;
   return KPN_OK;

@@ -1,0 +1,681 @@
+// Ray-march shading, engine 0: tcgen05 tensor-core MLPs with activations resident in tensor memory.
+//
+// One persistent CTA per SM, 9 warps:
+//   warps 0-3 : "row" warps of tile slot 0      warps 4-7 : row warps of tile slot 1
+//   warp 8    : TMEM allocator + TMA weight loader + the single thread that issues every tcgen05.mma
+// A tile is 128 rows = 4 warps x 32 lanes; a row is one (sample, source view) pair, the 3 views of a
+// sample sit in 3 adjacent lanes (10 samples per warp, 40 per tile), so every cross-view reduction of
+// the reference (view-weighted mean/variance pooling, src/utils.py:722-748; IBR blending weights, mean/var
+// and softmax, src/model.py:1286-1301) is a 3-lane shuffle.  Each row thread owns TMEM lane = its row:
+// it writes its layer inputs as packed fp16 straight into tensor memory (tcgen05.st), the MMA warp
+// multiplies them with the fp16 weights that stay resident in shared memory (loaded once per CTA with a
+// bulk TMA copy) into an fp32 accumulator in the other half of the slot's TMEM columns, and the row thread
+// reads its accumulator row back (tcgen05.ld), applies bias + activation in fp32 and overwrites it in
+// place with the next layer's fp16 input.  Activations never touch shared or global memory.  The two tile
+// slots ping-pong so the tensor pipe works on one tile while the CUDA cores run the other's epilogue.
+//
+// Stage table (A columns -> D columns inside the slot's 256 TMEM columns, R0 = [0,128), R1 = [128,256)):
+//   0 L0  190->128  A R0 D R1   1 L1 128->128 A R1 D R0   2 L2 136->120 A R0 D R1   3 L3 120->64 A R1 D R0
+//   4 P0|CMP 128->64|24 A R1 D R0   5 P1 64->64 A R0 D R1   (density head 64->2 stays fp32 on CUDA cores)
+//   6 BASE0 105->64 A R0 D R1   7 BASE1 64->32 A R1 D R0   8 VIS1A 32->32 A R0 D R1   9 VIS1B 32->33 A R1 D R0
+//   10 VIS2A 32->32 A R0 D R1   11 OUT0 37->16 A R1 D R0   (ray encoder, 32->1, 16->8->1 stay fp32 on CUDA cores)
+#include "kpn_device.cuh"
+#include "kpn_launch.h"
+#include "kpn_tc.cuh"
+#include "kpn_tc_types.cuh"
+
+namespace kpn {
+namespace {
+
+constexpr int ROW_WARPS = 4;
+constexpr int NSLOT = 2;
+constexpr int TC_THREADS = (NSLOT * ROW_WARPS + 2) * 32;  // 320: 8 row warps + hi issuer + lo issuer
+constexpr int SPW = 10;                                   // samples per warp (3 views each)
+constexpr int SPT = SPW * ROW_WARPS;                      // samples per tile
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Softplus(beta=100): max(x,0) + log1p(exp(-100|x|))/100  (reference src/utils.py:523-524; beyond the
+// reference's threshold the correction term is < 2e-11).
+__device__ __forceinline__ float sp_fast(float x) {
+  float e = ex2f(-100.0f * LOG2E * fabsf(x));
+  return fmaf(0.0069314718056f, lg2f(1.0f + e), fmaxf(x, 0.0f));
+}
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.0f ? x : ex2f(x * LOG2E) - 1.0f; }
+__device__ __forceinline__ float sig_fast(float x) { return rcpf(1.0f + ex2f(-x * LOG2E)); }
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+
+// two-term fp16 split of a pair of activations: hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(a, b);
+  float2 f = __half22float2(h);
+  __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// Scene constants the row threads need, staged once per CTA in shared memory (the per-view index differs per lane).
+struct SceneS {
+  float P[3][12];   // KRT rows
+  float E[3][12];   // extrinsic rows
+  float C[3][4];    // source camera centres
+  float4 kc[3][KPN_MAX_KPT];   // keypoints in camera space
+  float wm1, hm1, znear, inv_zrange, sp_scale, inv2sig2;
+  MapDesc f64, f8, ftex, img;
+};
+
+__device__ __forceinline__ Proj project_s(const SceneS& S, int v, const float p[3]) {
+  const float* P = S.P[v];
+  float hx = P[0] * p[0] + P[1] * p[1] + P[2] * p[2] + P[3];
+  float hy = P[4] * p[0] + P[5] * p[1] + P[6] * p[2] + P[7];
+  float hz = P[8] * p[0] + P[9] * p[1] + P[10] * p[2] + P[11];
+  Proj r;
+  r.u = 2.0f * ((hx / hz) / S.wm1) - 1.0f;
+  r.v = 2.0f * ((hy / hz) / S.hm1) - 1.0f;
+  r.zn = 2.0f * (hz - S.znear) * S.inv_zrange - 1.0f;
+  return r;
+}
+__device__ __forceinline__ float boundary_weight_fast(const Proj& q) {
+  float c[3] = {q.u, q.v, q.zn};
+  float w = 1.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float x = 0.5f * c[i] + 0.5f;
+    float db = fminf(x, 1.0f - x);
+    w *= sig_fast(fmaf(50.0f, db, -5.0f));   // sigmoid(5*(db/0.1 - 1)), reference src/model.py:755
+  }
+  return w;
+}
+
+struct RowCtx {
+  uint32_t R0, R1;      // TMEM addresses (lane field already set) of the slot's two column regions
+  uint64_t* a_ready;    // row threads -> MMA thread : "layer input is in TMEM"   (count 128)
+  uint64_t* acc_ready;  // MMA thread -> row threads : "accumulator is complete"  (tcgen05.commit)
+  uint32_t ph;          // parity of acc_ready this thread waits on next
+  int gb;               // first lane of this row's 3-view group
+  int l1, l2;           // the other two lanes of the group
+};
+
+__device__ __forceinline__ void signal_a(RowCtx& c) {
+  tc::wait_st();
+  tc::fence_before_sync();
+  tc::mbar_arrive(c.a_ready);
+}
+__device__ __forceinline__ void wait_acc(RowCtx& c) {
+  tc::mbar_wait(c.acc_ready, c.ph);
+  c.ph ^= 1u;
+  tc::fence_after_sync();
+}
+__device__ __forceinline__ float gsum(const RowCtx& c, float x) {
+  return x + __shfl_sync(FULL, x, c.l1) + __shfl_sync(FULL, x, c.l2);
+}
+__device__ __forceinline__ float gmin(const RowCtx& c, float x) {
+  return fminf(x, fminf(__shfl_sync(FULL, x, c.l1), __shfl_sync(FULL, x, c.l2)));
+}
+__device__ __forceinline__ float gmax(const RowCtx& c, float x) {
+  return fmaxf(x, fmaxf(__shfl_sync(FULL, x, c.l1), __shfl_sync(FULL, x, c.l2)));
+}
+
+// acc (NCH*32 fp32 columns at src) -> act(acc + bias) as packed fp16 at dst (in place allowed: dst <= src).
+template <int NCH, int ACT>  // ACT 1 = softplus100, 2 = ELU
+__device__ __forceinline__ void epi_inplace(uint32_t src, uint32_t dst, const float* __restrict__ bias) {
+  uint32_t r[2][32];
+  tc::tmem_ld32(src, r[0]);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    tc::wait_ld();
+    if (ch + 1 < NCH) tc::tmem_ld32(src + (ch + 1) * 32, r[(ch + 1) & 1]);   // next chunk in flight while this one is processed
+    uint32_t o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float x0 = u2f(r[ch & 1][2 * i]) + bias[ch * 32 + 2 * i], x1 = u2f(r[ch & 1][2 * i + 1]) + bias[ch * 32 + 2 * i + 1];
+      if (ACT == 1) { x0 = sp_fast(x0); x1 = sp_fast(x1); }
+      else { x0 = elu_fast(x0); x1 = elu_fast(x1); }
+      o[i] = tc::pack_h2(x0, x1);
+    }
+    tc::tmem_st16(dst + ch * 16, o);
+  }
+}
+
+// Keypoint encoding of one keypoint with sp_level == 3: sin/cos(pi*2^l*dz) from one sincos + double angles.
+__device__ __forceinline__ void encode_fast(const SceneS& S, int v, int k, const float c[3], float e[7]) {
+  const float4 kc = S.kc[v][k];
+  float dx = c[0] - kc.x, dy = c[1] - kc.y, dzc = c[2] - kc.z;
+  float dz = S.sp_scale * dzc;
+  float w = __expf(-(dx * dx + dy * dy + dzc * dzc) * S.inv2sig2);
+  float s, co;
+  __sincosf(dz * 3.14159265358979f, &s, &co);
+  float s2 = 2.0f * s * co, c2 = 1.0f - 2.0f * s * s;
+  float s4 = 2.0f * s2 * c2, c4 = 1.0f - 2.0f * s2 * s2;
+  e[0] = dz * w; e[1] = s * w; e[2] = co * w; e[3] = s2 * w; e[4] = c2 * w; e[5] = s4 * w; e[6] = c4 * w;
+}
+
+template <int NK>
+__device__ __forceinline__ void row_tile(const SceneS& sc, const TcConsts& C, const SampleSrc& src,
+                                         const int* __restrict__ list, int count, int tile, RowCtx& cx, int roww, int lane,
+                                         int query_mode, float* __restrict__ out5) {
+  constexpr int ENC = 7 * NK;
+  constexpr int A0C = tc_k0p(NK) / 2;
+  const uint32_t R0 = cx.R0, R1 = cx.R1;
+  const int g = lane / 3;
+  const int v = lane - 3 * g;           // lanes 30,31 replay views 0,1 of the warp's last sample (results unused)
+  const int si = tile * SPT + roww * SPW + min(g, SPW - 1);
+  const bool writer = (lane < 3 * SPW) && (v == 0) && (si < count);
+  const int id = list[min(si, count - 1)];
+  float p[3], d[3];
+  fetch_sample(src, id, p, d);
+  const Proj q = project_s(sc, v, p);
+  const float bw = boundary_weight_fast(q);
+  const float pw = bw / (gsum(cx, bw) + 1e-6f);  // reference src/model.py:750-759 (mask == 1 for shaded samples)
+
+  // ---- stage 0 input: [encoding 7*NK | feat64 64 | 0-pad] -> fp16 -> TMEM R0
+  {
+    uint32_t a[A0C];
+    float c[3];
+    {
+      const float* E = sc.E[v];
+      c[0] = E[0] * p[0] + E[1] * p[1] + E[2] * p[2] + E[3];
+      c[1] = E[4] * p[0] + E[5] * p[1] + E[6] * p[2] + E[7];
+      c[2] = E[8] * p[0] + E[9] * p[1] + E[10] * p[2] + E[11];
+    }
+#pragma unroll
+    for (int k = 0; k < NK; k += 2) {
+      float e0[7], e1[7];
+      encode_fast(sc, v, k, c, e0);
+      encode_fast(sc, v, k + 1, c, e1);
+#pragma unroll
+      for (int r = 0; r < 7; ++r) a[(r * NK + k) / 2] = tc::pack_h2(e0[r], e1[r]);
+    }
+    const Taps t64 = make_taps(q.u, q.v, sc.f64.W, sc.f64.H);
+#pragma unroll
+    for (int cq = 0; cq < 4; ++cq) {
+      float f[16];
+      gather_f32<4>(sc.f64, v, t64, cq * 4, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[ENC / 2 + cq * 8 + i] = tc::pack_h2(f[2 * i], f[2 * i + 1]);
+    }
+#pragma unroll
+    for (int i = ENC / 2 + 32; i < A0C; ++i) a[i] = 0u;
+#pragma unroll
+    for (int c0 = 0; c0 + 32 <= A0C; c0 += 32) tc::tmem_st32(R0 + c0, a + c0);
+    if (A0C % 32 >= 16) tc::tmem_st16(R0 + (A0C / 32) * 32, a + (A0C / 32) * 32);
+    if (A0C % 16 >= 8) tc::tmem_st8(R0 + (A0C / 16) * 16, a + (A0C / 16) * 16);
+  }
+  signal_a(cx);
+  // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720)
+  wait_acc(cx);
+  epi_inplace<4, 1>(R1, R1, C.b_l0);
+  signal_a(cx);
+  wait_acc(cx);
+  epi_inplace<4, 1>(R0, R0, C.b_l1);
+  {
+    const Taps t8 = make_taps(q.u, q.v, sc.f8.W, sc.f8.H);
+    float g8[8];
+    gather_f32<2>(sc.f8, v, t8, 0, g8);
+    uint32_t o[8] = {tc::pack_h2(g8[0], g8[1]), tc::pack_h2(g8[2], g8[3]), tc::pack_h2(g8[4], g8[5]), tc::pack_h2(g8[6], g8[7]),
+                     0u, 0u, 0u, 0u};
+    tc::tmem_st8(R0 + 64, o);
+  }
+  signal_a(cx);
+  wait_acc(cx);
+  epi_inplace<4, 1>(R1, R1, C.b_l2);
+  signal_a(cx);
+  // ---- view pooling: weighted mean || variance over the 3 lanes of the group (src/utils.py:722-748)
+  wait_acc(cx);
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t r[32];
+    tc::tmem_ld32(R0 + ch * 32, r);
+    tc::wait_ld();
+    uint32_t om[16], ov[16], lm[16], lv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float x0 = u2f(r[2 * i]) + C.b_l3[ch * 32 + 2 * i], x1 = u2f(r[2 * i + 1]) + C.b_l3[ch * 32 + 2 * i + 1];
+      float m0 = gsum(cx, pw * x0), m1 = gsum(cx, pw * x1);
+      float d0 = x0 - m0, d1 = x1 - m1;
+      float v0 = gsum(cx, pw * d0 * d0), v1 = gsum(cx, pw * d1 * d1);
+      split_h2(m0, m1, om[i], lm[i]);   // the density tail's inputs are kept to two fp16 terms (hi | lo)
+      split_h2(v0, v1, ov[i], lv[i]);
+    }
+    tc::tmem_st16(R1 + ch * 16, om);
+    tc::tmem_st16(R1 + 32 + ch * 16, ov);
+    tc::tmem_st16(R1 + 64 + ch * 16, lm);
+    tc::tmem_st16(R1 + 96 + ch * 16, lv);
+  }
+  signal_a(cx);
+  // ---- P0 (softplus) | compress (linear, kept in registers)  (src/utils.py:577-587, src/model.py:819)
+  wait_acc(cx);
+  float lat[24];
+  {
+    uint32_t r[32];
+    tc::tmem_ld32(R0 + 64, r);
+    tc::wait_ld();
+#pragma unroll
+    for (int i = 0; i < 24; ++i) lat[i] = u2f(r[i]) + C.b_cmp[i];
+  }
+  {
+    uint32_t r[64];
+    tc::tmem_ld32(R0, r);
+    tc::tmem_ld32(R0 + 32, r + 32);
+    tc::wait_ld();
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      split_h2(sp_fast(u2f(r[2 * i]) + C.b_p0[2 * i]), sp_fast(u2f(r[2 * i + 1]) + C.b_p0[2 * i + 1]), hi[i], lo[i]);
+    tc::tmem_st32(R0, hi);
+    tc::tmem_st32(R0 + 32, lo);
+  }
+  signal_a(cx);
+  // ---- P1 (softplus) then the 64->2 density head in fp32 on the CUDA cores
+  wait_acc(cx);
+  float g0 = C.b_p2[0], rad = C.b_p2[1];
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t r[32];
+    tc::tmem_ld32(R1 + ch * 32, r);
+    tc::wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float h = sp_fast(u2f(r[i]) + C.b_p1[ch * 32 + i]);
+      g0 = fmaf(C.w_p2[0][ch * 32 + i], h, g0);
+      rad = fmaf(C.w_p2[1][ch * 32 + i], h, rad);
+    }
+  }
+  // ---- colour branch inputs (src/model.py:806-832)
+  float rgb[3], f[35], rd[4];
+  {
+    const Taps ti = make_taps(q.u, q.v, sc.img.W, sc.img.H);
+    float c4[4];
+    gather_f32<1>(sc.img, v, ti, 0, c4);
+    rgb[0] = c4[0]; rgb[1] = c4[1]; rgb[2] = c4[2];
+    f[0] = c4[0]; f[1] = c4[1]; f[2] = c4[2];
+    const Taps tt = make_taps(q.u, q.v, sc.ftex.W, sc.ftex.H);
+    float t8[8];
+    gather_f32<2>(sc.ftex, v, tt, 0, t8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[3 + i] = t8[i];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) f[11 + i] = lat[i];
+    {  // [unit(dir - dir_src), dir . dir_src], reference src/model.py:825-832
+      float r[3] = {p[0] - sc.C[v][0], p[1] - sc.C[v][1], p[2] - sc.C[v][2]};
+      float n = fmaxf(sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]), 1e-12f);
+      r[0] /= n; r[1] /= n; r[2] /= n;
+      float e[3] = {d[0] - r[0], d[1] - r[1], d[2] - r[2]};
+      float en = fmaxf(sqrtf(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]), 1e-6f);
+      rd[0] = e[0] / en; rd[1] = e[1] / en; rd[2] = e[2] / en;
+      rd[3] = r[0] * d[0] + r[1] * d[1] + r[2] * d[2];
+    }
+  }
+  {  // ray-direction encoder 4->16->35, ELU, added onto the features (src/model.py:1279-1284); fp32
+    float h16[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      float acc = C.b_re0[o];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc = fmaf(C.w_re0[o][i], rd[i], acc);
+      h16[o] = elu_fast(acc);
+    }
+#pragma unroll
+    for (int o = 0; o < 35; ++o) {
+      float acc = C.b_re1[o];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc = fmaf(C.w_re1[o][i], h16[i], acc);
+      f[o] += elu_fast(acc);
+    }
+  }
+  float om;  // blending weight (src/model.py:1286-1289), mask == 1
+  {
+    float ex = ex2f(C.ani_abs * LOG2E * (rd[3] - 1.0f));
+    float e = ex - gmin(cx, ex);
+    om = e / (gsum(cx, e) + 1e-8f);
+  }
+  {  // BASE0 input [mean35 | var35 | f35 | 0-pad] (src/model.py:1291-1292)
+    float mean[35], var[35];
+#pragma unroll
+    for (int c = 0; c < 35; ++c) {
+      mean[c] = gsum(cx, om * f[c]);
+      float dl = f[c] - mean[c];
+      var[c] = gsum(cx, om * dl * dl);
+    }
+    uint32_t a[56];
+#pragma unroll
+    for (int j = 0; j < 56; ++j) {
+      const int e0 = 2 * j, e1 = 2 * j + 1;
+      float x0 = e0 < 35 ? mean[e0 < 35 ? e0 : 0] : e0 < 70 ? var[e0 < 70 ? (e0 >= 35 ? e0 - 35 : 0) : 0]
+                 : e0 < 105 ? f[e0 >= 70 ? (e0 < 105 ? e0 - 70 : 0) : 0] : 0.0f;
+      float x1 = e1 < 35 ? mean[e1 < 35 ? e1 : 0] : e1 < 70 ? var[e1 < 70 ? (e1 >= 35 ? e1 - 35 : 0) : 0]
+                 : e1 < 105 ? f[e1 >= 70 ? (e1 < 105 ? e1 - 70 : 0) : 0] : 0.0f;
+      a[j] = tc::pack_h2(x0, x1);
+    }
+    tc::tmem_st32(R0, a);
+    tc::tmem_st16(R0 + 32, a + 32);
+    tc::tmem_st8(R0 + 48, a + 48);
+  }
+  signal_a(cx);
+  // ---- BASE0 -> BASE1
+  wait_acc(cx);
+  epi_inplace<2, 2>(R1, R1, C.b_base0);
+  signal_a(cx);
+  wait_acc(cx);
+  float x[32];
+  {
+    uint32_t r[32];
+    tc::tmem_ld32(R0, r);
+    tc::wait_ld();
+    uint32_t o[16];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = elu_fast(u2f(r[i]) + C.b_base1[i]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = tc::pack_h2(x[2 * i] * om, x[2 * i + 1] * om);  // vis_layer1(x * weight)
+    tc::tmem_st16(R0, o);
+  }
+  signal_a(cx);
+  // ---- VIS1A -> VIS1B (src/model.py:1294-1296)
+  wait_acc(cx);
+  epi_inplace<1, 2>(R1, R1, C.b_vis1a);
+  signal_a(cx);
+  wait_acc(cx);
+  {
+    uint32_t r[32], r2[16];
+    tc::tmem_ld32(R0, r);
+    tc::tmem_ld16(R0 + 32, r2);
+    tc::wait_ld();
+    float sg = sig_fast(elu_fast(u2f(r2[0]) + C.b_vis1b[32]));
+    uint32_t o[16];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] += elu_fast(u2f(r[i]) + C.b_vis1b[i]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = tc::pack_h2(x[2 * i] * sg, x[2 * i + 1] * sg);  // x * sigmoid(vis) * mask
+    tc::tmem_st16(R0, o);
+  }
+  signal_a(cx);
+  // ---- VIS2A (+ 32->1 sigmoid on CUDA cores) -> OUT0 input [x32 | vis | ray_diff4 | 0-pad] (src/model.py:1297-1300)
+  wait_acc(cx);
+  {
+    uint32_t r[32];
+    tc::tmem_ld32(R1, r);
+    tc::wait_ld();
+    float dot = C.b_vis2b;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dot = fmaf(C.w_vis2b[i], elu_fast(u2f(r[i]) + C.b_vis2a[i]), dot);
+    float vis2 = sig_fast(dot);
+    uint32_t o[24];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = tc::pack_h2(x[2 * i], x[2 * i + 1]);
+    o[16] = tc::pack_h2(vis2, rd[0]);
+    o[17] = tc::pack_h2(rd[1], rd[2]);
+    o[18] = tc::pack_h2(rd[3], 0.0f);
+#pragma unroll
+    for (int i = 19; i < 24; ++i) o[i] = 0u;
+    tc::tmem_st16(R1, o);
+    tc::tmem_st8(R1 + 16, o + 16);
+  }
+  signal_a(cx);
+  // ---- OUT0 -> 16->8->1 on CUDA cores -> softmax over the views -> blended colour (src/model.py:1300-1301)
+  wait_acc(cx);
+  float logit;
+  {
+    uint32_t r[16];
+    tc::tmem_ld16(R0, r);
+    tc::wait_ld();
+    float h16[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h16[i] = elu_fast(u2f(r[i]) + C.b_out0[i]);
+    logit = C.b_out2;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float acc = C.b_out1[o];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc = fmaf(C.w_out1[o][i], h16[i], acc);
+      logit = fmaf(C.w_out2[o], elu_fast(acc), logit);
+    }
+  }
+  {
+    float e = ex2f((logit - gmax(cx, logit)) * LOG2E);
+    float inv = 1.0f / gsum(cx, e);
+    float r0 = gsum(cx, e * rgb[0]) * inv, r1 = gsum(cx, e * rgb[1]) * inv, r2 = gsum(cx, e * rgb[2]) * inv;
+    if (writer) {
+      float* o = out5 + 5ll * id;
+      if (query_mode) { o[0] = g0; o[1] = rad; }
+      else { o[0] = fmaxf(rad, 0.0f); o[1] = g0; }   // eval_func, src/model.py:978-997
+      o[2] = r0; o[3] = r1; o[4] = r2;
+    }
+  }
+}
+
+// Precision: the geometry/density weights (stages 0..5) are applied as W = W_hi + W_lo, two fp16 terms.  W_hi stays
+// resident in shared memory; W_lo (the rounding residual of W_hi) is streamed from L2 through a small ring of 4 KB
+// slots with bulk TMA copies, one slot per 16-row K step, and accumulated into the same TMEM accumulator.  This removes
+// the weight-rounding error, which is systematic along a ray and dominated the RGB error of a plain fp16 pipeline
+// (DESIGN.md "precision"); the tensor pipe has the headroom, the CUDA cores are the bottleneck.
+constexpr int TC_NLO = 6;          // stages with a W_lo pass
+constexpr uint32_t RING_SLOT = 4096;
+
+struct LoRing {
+  uint32_t base;        // shared address of slot 0
+  uint8_t* base_ptr;
+  uint64_t* full;       // [NRING] TMA -> MMA
+  uint64_t* empty;      // [NRING] MMA (tcgen05.commit) -> TMA
+  uint32_t full_par, empty_par;   // one parity bit per slot
+  int head, n;
+};
+
+__device__ __forceinline__ void ring_load(LoRing& rg, int r, const uint8_t* gsrc, uint32_t bytes) {
+  tc::mbar_wait(&rg.empty[r], ((rg.empty_par >> r) & 1u) ^ 1u);   // slot free (passes immediately the first time)
+  rg.empty_par ^= 1u << r;
+  tc::mbar_expect_tx(&rg.full[r], bytes);
+  tc::bulk_g2s(rg.base_ptr + (size_t)r * RING_SLOT, gsrc, bytes, &rg.full[r]);
+}
+
+__device__ __forceinline__ void issue_stage_lo(uint32_t slot_tm, LoRing& rg, const uint8_t* __restrict__ wlo, const TcPlan& plan,
+                                               int stage) {
+  const uint32_t a_r1 = (0xA9Au >> stage) & 1u;
+  const uint32_t a_tm = slot_tm + (a_r1 ? 128u : 0u), d_tm = slot_tm + (a_r1 ? 0u : 128u);
+  const int Np = plan.st[stage].Np, nk = plan.st[stage].Kp / 16;
+  const uint32_t lbo = (uint32_t)(Np / 8) * 128u, bytes = 2u * lbo;
+  const uint32_t idesc = tc::make_idesc_f16(128, Np);
+  const uint8_t* src = wlo + plan.st[stage].off;
+  const int pf = nk < rg.n ? nk : rg.n;
+  for (int j = 0; j < pf; ++j) ring_load(rg, (rg.head + j) % rg.n, src + (size_t)j * bytes, bytes);
+  for (int j = 0; j < nk; ++j) {
+    const int r = (rg.head + j) % rg.n;
+    tc::mbar_wait(&rg.full[r], (rg.full_par >> r) & 1u);
+    rg.full_par ^= 1u << r;
+    uint64_t bd = tc::make_smem_desc(rg.base + (uint32_t)r * RING_SLOT, lbo, 128u);
+    tc::mma_ts(d_tm, a_tm + (uint32_t)j * 8u, bd, idesc, 1u);
+    tc::mma_commit(&rg.empty[r]);
+    if (j + pf < nk) ring_load(rg, (rg.head + j + pf) % rg.n, src + (size_t)(j + pf) * bytes, bytes);
+  }
+  rg.head = (rg.head + nk) % rg.n;
+}
+
+__device__ __forceinline__ void issue_stage(uint32_t slot_tm, uint32_t wsmem, const TcPlan& plan, int stage) {
+  // which TMEM region holds the stage's A operand (1 = R1); D goes to the other one
+  const uint32_t a_r1 = (0xA9Au >> stage) & 1u;  // bits: stages 1,3,4,7,9,11
+  const uint32_t a_tm = slot_tm + (a_r1 ? 128u : 0u), d_tm = slot_tm + (a_r1 ? 0u : 128u);
+  const int Kp = plan.st[stage].Kp, Np = plan.st[stage].Np;
+  const uint32_t lbo = (uint32_t)(Np / 8) * 128u;
+  const uint32_t idesc = tc::make_idesc_f16(128, Np);
+  const uint32_t b0 = wsmem + plan.st[stage].off;
+  for (int j = 0; j < Kp / 16; ++j) {
+    uint64_t bd = tc::make_smem_desc(b0 + (uint32_t)j * 2u * lbo, lbo, 128u);
+    tc::mma_ts(d_tm, a_tm + (uint32_t)j * 8u, bd, idesc, j > 0 ? 1u : 0u);
+  }
+  // density tail (stages 4, 5): the activations come as hi | lo, the lo half sits Kp/2 columns further
+  if (stage == 4 || stage == 5) {
+    for (int j = 0; j < Kp / 16; ++j) {
+      uint64_t bd = tc::make_smem_desc(b0 + (uint32_t)j * 2u * lbo, lbo, 128u);
+      tc::mma_ts(d_tm, a_tm + (uint32_t)(Kp / 2) + (uint32_t)j * 8u, bd, idesc, 1u);
+    }
+  }
+}
+
+template <int NK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
+                const uint8_t* __restrict__ wlo, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr, int query_mode,
+                float* __restrict__ out5) {
+  extern __shared__ __align__(1024) uint8_t wsm[];
+  constexpr int NRING = NK <= 18 ? 6 : 3;
+  // barriers: [0] weights | per slot s: [1+3s] a_ready (128 row threads), [2+3s] acc_ready (2 commits: hi issuer + lo issuer),
+  //           [3+3s] hi_issued (hi issuer -> lo issuer: "the accumulator-initialising MMAs are in the pipe") | TMA ring full/empty
+  __shared__ uint64_t bars[1 + 3 * NSLOT + 2 * NRING];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ SceneS scs;
+  constexpr TcPlan plan = make_tc_plan(NK);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int count = *count_ptr;
+  {
+    const DevScene& g = *scp;
+    for (int i = t; i < 3 * 12; i += TC_THREADS) { scs.P[i / 12][i % 12] = g.P[i / 12][i % 12]; scs.E[i / 12][i % 12] = g.E[i / 12][i % 12]; }
+    for (int i = t; i < 3 * 3; i += TC_THREADS) scs.C[i / 3][i % 3] = g.C[i / 3][i % 3];
+    for (int i = t; i < 3 * NK; i += TC_THREADS)
+      scs.kc[i / NK][i % NK] = make_float4(g.kc[i / NK][i % NK][0], g.kc[i / NK][i % NK][1], g.kc[i / NK][i % NK][2], 0.0f);
+    if (t == 0) {
+      scs.wm1 = g.wm1; scs.hm1 = g.hm1; scs.znear = g.znear; scs.inv_zrange = 1.0f / (g.zfar - g.znear);
+      scs.sp_scale = g.sp_scale; scs.inv2sig2 = g.inv2sig2;
+      scs.f64 = g.f64; scs.f8 = g.f8; scs.ftex = g.ftex; scs.img = g.img;
+    }
+  }
+  const int ntiles = (count + SPT - 1) / SPT;
+  uint64_t* wbar = &bars[0];
+  const bool two_term = wlo != nullptr;
+
+  if (warp == 8) tc::tmem_alloc(&tmem_base_s, 512);
+  if (t == 0) {
+    tc::mbar_init(wbar, 1);
+    for (int s = 0; s < NSLOT; ++s) {
+      tc::mbar_init(&bars[1 + 3 * s], ROW_WARPS * 32);
+      tc::mbar_init(&bars[2 + 3 * s], 2);
+      tc::mbar_init(&bars[3 + 3 * s], 1);
+    }
+    for (int r = 0; r < 2 * NRING; ++r) tc::mbar_init(&bars[1 + 3 * NSLOT + r], 1);
+    tc::fence_mbar_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  // tiles of this CTA: slot s takes tile (i*gridDim.x + blockIdx.x)*NSLOT + s
+  auto tiles_of_slot = [&](int s) {
+    int n = 0;
+    for (int tile = blockIdx.x * NSLOT + s; tile < ntiles; tile += gridDim.x * NSLOT) ++n;
+    return n;
+  };
+
+  if (warp == 8) {
+    // ---- hi issuer: resident W_hi tiles; initialises the accumulator of every stage
+    if (lane == 0 && ntiles > 0) {
+      tc::mbar_expect_tx(wbar, plan.total_bytes);
+      for (uint32_t off = 0; off < plan.total_bytes; off += 32768u) {
+        uint32_t n = plan.total_bytes - off < 32768u ? plan.total_bytes - off : 32768u;
+        tc::bulk_g2s(wsm + off, wblob + off, n, wbar);
+      }
+      tc::mbar_wait(wbar, 0);
+      const uint32_t wsmem = tc::smem_u32(wsm);
+      int remaining[NSLOT], stage[NSLOT];
+      uint32_t par[NSLOT];
+      for (int s = 0; s < NSLOT; ++s) { remaining[s] = tiles_of_slot(s) * TC_NSTAGE; stage[s] = 0; par[s] = 0; }
+      while (remaining[0] > 0 || remaining[1] > 0) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          if (remaining[s] > 0 && tc::mbar_try_wait(&bars[1 + 3 * s], par[s])) {
+            tc::fence_after_sync();
+            issue_stage(tbase + (uint32_t)s * 256u, wsmem, plan, stage[s]);
+            const bool lo_follows = two_term && stage[s] < TC_NLO;
+            if (lo_follows) tc::mbar_arrive(&bars[3 + 3 * s]);      // lo issuer may now accumulate on top
+            else tc::mbar_arrive(&bars[2 + 3 * s]);                  // no lo pass: stand in for its commit
+            tc::mma_commit(&bars[2 + 3 * s]);
+            par[s] ^= 1u;
+            stage[s] = stage[s] + 1 == TC_NSTAGE ? 0 : stage[s] + 1;
+            --remaining[s];
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ---- lo issuer: streams the W_lo tiles of stages 0..5 from L2 through its own TMA ring
+    if (lane == 0 && ntiles > 0 && two_term) {
+      LoRing rg;
+      rg.base_ptr = wsm + plan.total_bytes;
+      rg.base = tc::smem_u32(rg.base_ptr);
+      rg.full = &bars[1 + 3 * NSLOT];
+      rg.empty = &bars[1 + 3 * NSLOT + NRING];
+      rg.full_par = 0; rg.empty_par = 0; rg.head = 0; rg.n = NRING;
+      // triggered only by hi_issued (one phase per precise stage; the next one cannot happen before this
+      // thread's commit lets the rows proceed, so the parity wait can never alias)
+      int remaining[NSLOT], stage[NSLOT];
+      uint32_t par_hi[NSLOT];
+      for (int s = 0; s < NSLOT; ++s) { remaining[s] = tiles_of_slot(s) * TC_NLO; stage[s] = 0; par_hi[s] = 0; }
+      while (remaining[0] > 0 || remaining[1] > 0) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          if (remaining[s] > 0 && tc::mbar_try_wait(&bars[3 + 3 * s], par_hi[s])) {
+            par_hi[s] ^= 1u;
+            tc::fence_after_sync();
+            issue_stage_lo(tbase + (uint32_t)s * 256u, rg, wlo, plan, stage[s]);
+            tc::mma_commit(&bars[2 + 3 * s]);
+            stage[s] = stage[s] + 1 == TC_NLO ? 0 : stage[s] + 1;
+            --remaining[s];
+          }
+        }
+      }
+    }
+  } else {
+    const int slot = warp / ROW_WARPS, roww = warp % ROW_WARPS;
+    RowCtx cx;
+    const uint32_t tm = tbase + (uint32_t)slot * 256u + ((uint32_t)(roww * 32) << 16);
+    cx.R0 = tm; cx.R1 = tm + 128u;
+    cx.a_ready = &bars[1 + 3 * slot];
+    cx.acc_ready = &bars[2 + 3 * slot];
+    cx.ph = 0;
+    cx.gb = 3 * (lane / 3);
+    cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
+    cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
+    for (int tile = blockIdx.x * NSLOT + slot; tile < ntiles; tile += gridDim.x * NSLOT)
+      row_tile<NK>(scs, C, src, list, count, tile, cx, roww, lane, query_mode, out5);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tbase, 512);
+}
+
+}  // namespace
+
+size_t tc_weight_blob_bytes(int n_kpt) { return make_tc_plan(n_kpt).total_bytes; }
+size_t tc_weight_lo_bytes(int n_kpt) { return make_tc_plan(n_kpt).st[TC_NLO].off; }
+bool tc_supported(int n_views, int n_kpt, int sp_level) { return n_views == 3 && (n_kpt == 18 || n_kpt == 24) && sp_level == 3; }
+
+cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wlo, int n_kpt, const SampleSrc& src,
+                            const int* list, const int* counter, long long n_max, int query_mode, float* out5, int num_sms,
+                            cudaStream_t st) {
+  const size_t smem = tc_weight_blob_bytes(n_kpt) + (size_t)(n_kpt <= 18 ? 6 : 3) * RING_SLOT;
+  long long max_tiles = (n_max + SPT - 1) / SPT;
+  long long g = (max_tiles + NSLOT - 1) / NSLOT;
+  int grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
+  cudaError_t e;
+  if (n_kpt == 18) {
+    static bool attr18 = false;
+    if (!attr18) {
+      e = cudaFuncSetAttribute(shade_tc_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr18 = true;
+    }
+    shade_tc_kernel<18><<<grid, TC_THREADS, smem, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5);
+  } else {
+    static bool attr24 = false;
+    if (!attr24) {
+      e = cudaFuncSetAttribute(shade_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr24 = true;
+    }
+    shade_tc_kernel<24><<<grid, TC_THREADS, smem, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace kpn

@@ -199,7 +199,9 @@ class KeypointNeRF(nn.Module):
 
     def marcher_dtype(self) -> str:
         """Arithmetic type of the dense layers in the selected engine."""
-        return "fp32"
+        sp = self.sp_encoder
+        tc = self.engine != 1 and sp.n_kpt in (18, 24) and sp.sp_level == 3
+        return "fp16 operands, fp32 accumulate (tcgen05)" if tc else "fp32"
 
     def _bind_scene(self, cam, feat_geo, feat_tex, sp_data, img, fg_mask, bounds):
         m = self.marcher()
