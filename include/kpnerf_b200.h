@@ -166,6 +166,11 @@ int kpn_query(kpn_ctx* ctx, const float* pts, const float* view, int n, float* o
  * kpn_get_stats when profiling is on).  Synchronises `stream` (debug/bench only). */
 int kpn_get_stats(kpn_ctx* ctx, kpn_stats* stats, void* stream);
 
+/* Debug: per-stage barrier-wait cycles of one row warp per CTA of the tensor-core kernel.  out16 (host, may be NULL)
+ * receives [0..11] wait cycles at the 12 stages, [12] total tile cycles, [13] tiles recorded; then the counters are
+ * reset (enable != 0) or freed (enable == 0).  Synchronises the device. */
+int kpn_debug_timing(kpn_ctx* ctx, int enable, unsigned long long* out16);
+
 /* enable != 0: bracket every shading-kernel launch with CUDA events on its stream (no sync). */
 int kpn_set_profiling(kpn_ctx* ctx, int enable);
 

@@ -71,6 +71,7 @@ struct kpn_ctx {
   DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in;
   unsigned long long launches = 0;
   bool profiling = false;
+  unsigned long long* d_timing = nullptr;   // [16] debug: per-stage wait cycles of the tensor-core row warps
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   size_t ev_used = 0;
 };
@@ -341,7 +342,7 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_
   }
   if (use_tc)
     KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), engine == 2 ? nullptr : c->wlo.as<uint8_t>(), c->n_kpt,
-                                src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->num_sms, st));
+                                src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->num_sms, st, c->d_timing));
   else
     KPN_CUDA(c, launch_shade_simt(c->d_scene, c->d_wf32, src, c->ws_list.as<int>(), counter, n, query_mode, out5,
                                   c->num_sms, st));
@@ -526,6 +527,19 @@ extern "C" int kpn_get_stats(kpn_ctx* c, kpn_stats* stats, void* stream) {
   stats->shade_launches = c->ev_used / 2;
   stats->shade_ms = ms;
   c->ev_used = 0;
+  return KPN_OK;
+}
+
+extern "C" int kpn_debug_timing(kpn_ctx* c, int enable, unsigned long long* out16) {
+  if (!c) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  if (out16 && c->d_timing) {
+    KPN_CUDA(c, cudaDeviceSynchronize());
+    KPN_CUDA(c, cudaMemcpy(out16, c->d_timing, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  if (enable && !c->d_timing) KPN_CUDA(c, cudaMalloc(&c->d_timing, 16 * sizeof(unsigned long long)));
+  if (enable) KPN_CUDA(c, cudaMemset(c->d_timing, 0, 16 * sizeof(unsigned long long)));
+  if (!enable && c->d_timing) { cudaFree(c->d_timing); c->d_timing = nullptr; }
   return KPN_OK;
 }
 

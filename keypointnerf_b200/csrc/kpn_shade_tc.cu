@@ -29,7 +29,7 @@ namespace {
 
 constexpr int ROW_WARPS = 4;
 constexpr int NSLOT = 2;
-constexpr int TC_THREADS = (NSLOT * ROW_WARPS + 2) * 32;  // 320: 8 row warps + hi issuer + lo issuer
+constexpr int TC_THREADS = (NSLOT * ROW_WARPS + 3) * 32;  // 352: 8 row warps + hi issuer + one lo issuer per slot
 constexpr int SPW = 10;                                   // samples per warp (3 views each)
 constexpr int SPT = SPW * ROW_WARPS;                      // samples per tile
 constexpr float LOG2E = 1.4426950408889634f;
@@ -98,6 +98,8 @@ struct RowCtx {
   uint32_t ph;          // parity of acc_ready this thread waits on next
   int gb;               // first lane of this row's 3-view group
   int l1, l2;           // the other two lanes of the group
+  unsigned long long* tim;  // optional debug timing accumulators (only one recording thread per CTA slot 0)
+  int st;               // stage counter for the timing
 };
 
 __device__ __forceinline__ void signal_a(RowCtx& c) {
@@ -106,9 +108,11 @@ __device__ __forceinline__ void signal_a(RowCtx& c) {
   tc::mbar_arrive(c.a_ready);
 }
 __device__ __forceinline__ void wait_acc(RowCtx& c) {
+  long long t0 = c.tim ? clock64() : 0;
   tc::mbar_wait(c.acc_ready, c.ph);
   c.ph ^= 1u;
   tc::fence_after_sync();
+  if (c.tim) { atomicAdd(&c.tim[c.st], (unsigned long long)(clock64() - t0)); c.st = c.st + 1 == TC_NSTAGE ? 0 : c.st + 1; }
 }
 __device__ __forceinline__ float gsum(const RowCtx& c, float x) {
   return x + __shfl_sync(FULL, x, c.l1) + __shfl_sync(FULL, x, c.l2);
@@ -471,16 +475,24 @@ __device__ __forceinline__ void ring_load(LoRing& rg, int r, const uint8_t* gsrc
   tc::bulk_g2s(rg.base_ptr + (size_t)r * RING_SLOT, gsrc, bytes, &rg.full[r]);
 }
 
+// Number of leading chunks of `stage` already requested by ring_prefetch().
+__device__ __forceinline__ int ring_prefetch(LoRing& rg, const uint8_t* __restrict__ wlo, const TcPlan& plan, int stage) {
+  const int Np = plan.st[stage].Np, nk = plan.st[stage].Kp / 16;
+  const uint32_t bytes = 2u * (uint32_t)(Np / 8) * 128u;
+  const uint8_t* src = wlo + plan.st[stage].off;
+  const int pf = nk < rg.n ? nk : rg.n;
+  for (int j = 0; j < pf; ++j) ring_load(rg, (rg.head + j) % rg.n, src + (size_t)j * bytes, bytes);
+  return pf;
+}
+
 __device__ __forceinline__ void issue_stage_lo(uint32_t slot_tm, LoRing& rg, const uint8_t* __restrict__ wlo, const TcPlan& plan,
-                                               int stage) {
+                                               int stage, int pf) {
   const uint32_t a_r1 = (0xA9Au >> stage) & 1u;
   const uint32_t a_tm = slot_tm + (a_r1 ? 128u : 0u), d_tm = slot_tm + (a_r1 ? 0u : 128u);
   const int Np = plan.st[stage].Np, nk = plan.st[stage].Kp / 16;
   const uint32_t lbo = (uint32_t)(Np / 8) * 128u, bytes = 2u * lbo;
   const uint32_t idesc = tc::make_idesc_f16(128, Np);
   const uint8_t* src = wlo + plan.st[stage].off;
-  const int pf = nk < rg.n ? nk : rg.n;
-  for (int j = 0; j < pf; ++j) ring_load(rg, (rg.head + j) % rg.n, src + (size_t)j * bytes, bytes);
   for (int j = 0; j < nk; ++j) {
     const int r = (rg.head + j) % rg.n;
     tc::mbar_wait(&rg.full[r], (rg.full_par >> r) & 1u);
@@ -518,9 +530,9 @@ template <int NK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
                 const uint8_t* __restrict__ wlo, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr, int query_mode,
-                float* __restrict__ out5) {
+                float* __restrict__ out5, unsigned long long* __restrict__ timing) {
   extern __shared__ __align__(1024) uint8_t wsm[];
-  constexpr int NRING = NK <= 18 ? 6 : 3;
+  constexpr int NRING = NK <= 18 ? 6 : 2;   // TMA ring slots (4 KB each), split evenly between the two lo issuers
   // barriers: [0] weights | per slot s: [1+3s] a_ready (128 row threads), [2+3s] acc_ready (2 commits: hi issuer + lo issuer),
   //           [3+3s] hi_issued (hi issuer -> lo issuer: "the accumulator-initialising MMAs are in the pipe") | TMA ring full/empty
   __shared__ uint64_t bars[1 + 3 * NSLOT + 2 * NRING];
@@ -583,7 +595,7 @@ shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCons
       while (remaining[0] > 0 || remaining[1] > 0) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-          if (remaining[s] > 0 && tc::mbar_try_wait(&bars[1 + 3 * s], par[s])) {
+          if (remaining[s] > 0 && tc::mbar_test_wait(&bars[1 + 3 * s], par[s])) {
             tc::fence_after_sync();
             issue_stage(tbase + (uint32_t)s * 256u, wsmem, plan, stage[s]);
             const bool lo_follows = two_term && stage[s] < TC_NLO;
@@ -597,32 +609,32 @@ shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCons
         }
       }
     }
-  } else if (warp == 9) {
-    // ---- lo issuer: streams the W_lo tiles of stages 0..5 from L2 through its own TMA ring
-    if (lane == 0 && ntiles > 0 && two_term) {
+  } else if (warp == 9 || warp == 10) {
+    // ---- lo issuers (one per slot): stream the W_lo tiles of stages 0..5 from L2 through a private TMA ring.
+    // The chunks of the NEXT precise stage are requested as soon as the current one is committed (weights do not
+    // depend on the data), so their L2 latency hides behind the rows' epilogue.
+    const int s = warp - 9;
+    const int my_tiles = tiles_of_slot(s);
+    if (lane == 0 && my_tiles > 0 && two_term) {
+      constexpr int NR = NRING / NSLOT;
       LoRing rg;
-      rg.base_ptr = wsm + plan.total_bytes;
+      rg.base_ptr = wsm + plan.total_bytes + (size_t)s * NR * RING_SLOT;
       rg.base = tc::smem_u32(rg.base_ptr);
-      rg.full = &bars[1 + 3 * NSLOT];
-      rg.empty = &bars[1 + 3 * NSLOT + NRING];
-      rg.full_par = 0; rg.empty_par = 0; rg.head = 0; rg.n = NRING;
-      // triggered only by hi_issued (one phase per precise stage; the next one cannot happen before this
-      // thread's commit lets the rows proceed, so the parity wait can never alias)
-      int remaining[NSLOT], stage[NSLOT];
-      uint32_t par_hi[NSLOT];
-      for (int s = 0; s < NSLOT; ++s) { remaining[s] = tiles_of_slot(s) * TC_NLO; stage[s] = 0; par_hi[s] = 0; }
-      while (remaining[0] > 0 || remaining[1] > 0) {
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-          if (remaining[s] > 0 && tc::mbar_try_wait(&bars[3 + 3 * s], par_hi[s])) {
-            par_hi[s] ^= 1u;
-            tc::fence_after_sync();
-            issue_stage_lo(tbase + (uint32_t)s * 256u, rg, wlo, plan, stage[s]);
-            tc::mma_commit(&bars[2 + 3 * s]);
-            stage[s] = stage[s] + 1 == TC_NLO ? 0 : stage[s] + 1;
-            --remaining[s];
-          }
-        }
+      rg.full = &bars[1 + 3 * NSLOT + s * NR];
+      rg.empty = &bars[1 + 3 * NSLOT + NRING + s * NR];
+      rg.full_par = 0; rg.empty_par = 0; rg.head = 0; rg.n = NR;
+      int remaining = my_tiles * TC_NLO, stage = 0;
+      uint32_t par_hi = 0;
+      int pf = ring_prefetch(rg, wlo, plan, 0);
+      while (remaining > 0) {
+        tc::mbar_wait(&bars[3 + 3 * s], par_hi);   // hi issuer has put the accumulator-initialising MMAs in the pipe
+        par_hi ^= 1u;
+        tc::fence_after_sync();
+        issue_stage_lo(tbase + (uint32_t)s * 256u, rg, wlo, plan, stage, pf);
+        tc::mma_commit(&bars[2 + 3 * s]);
+        stage = stage + 1 == TC_NLO ? 0 : stage + 1;
+        --remaining;
+        pf = remaining > 0 ? ring_prefetch(rg, wlo, plan, stage) : 0;
       }
     }
   } else {
@@ -636,8 +648,13 @@ shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCons
     cx.gb = 3 * (lane / 3);
     cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
     cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
-    for (int tile = blockIdx.x * NSLOT + slot; tile < ntiles; tile += gridDim.x * NSLOT)
+    cx.tim = (timing != nullptr && warp == 0 && lane == 0) ? timing : nullptr;
+    cx.st = 0;
+    for (int tile = blockIdx.x * NSLOT + slot; tile < ntiles; tile += gridDim.x * NSLOT) {
+      long long t0 = cx.tim ? clock64() : 0;
       row_tile<NK>(scs, C, src, list, count, tile, cx, roww, lane, query_mode, out5);
+      if (cx.tim) { atomicAdd(&cx.tim[12], (unsigned long long)(clock64() - t0)); atomicAdd(&cx.tim[13], 1ull); }
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -652,8 +669,8 @@ bool tc_supported(int n_views, int n_kpt, int sp_level) { return n_views == 3 &&
 
 cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wlo, int n_kpt, const SampleSrc& src,
                             const int* list, const int* counter, long long n_max, int query_mode, float* out5, int num_sms,
-                            cudaStream_t st) {
-  const size_t smem = tc_weight_blob_bytes(n_kpt) + (size_t)(n_kpt <= 18 ? 6 : 3) * RING_SLOT;
+                            cudaStream_t st, unsigned long long* timing) {
+  const size_t smem = tc_weight_blob_bytes(n_kpt) + (size_t)(n_kpt <= 18 ? 6 : 2) * RING_SLOT;
   long long max_tiles = (n_max + SPT - 1) / SPT;
   long long g = (max_tiles + NSLOT - 1) / NSLOT;
   int grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
@@ -665,7 +682,7 @@ cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t
       if (e != cudaSuccess) return e;
       attr18 = true;
     }
-    shade_tc_kernel<18><<<grid, TC_THREADS, smem, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5);
+    shade_tc_kernel<18><<<grid, TC_THREADS, smem, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5, timing);
   } else {
     static bool attr24 = false;
     if (!attr24) {
@@ -673,7 +690,7 @@ cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t
       if (e != cudaSuccess) return e;
       attr24 = true;
     }
-    shade_tc_kernel<24><<<grid, TC_THREADS, smem, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5);
+    shade_tc_kernel<24><<<grid, TC_THREADS, smem, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5, timing);
   }
   return cudaGetLastError();
 }
