@@ -61,14 +61,15 @@ struct kpn_ctx {
   TcConsts tcc;                // fp32 constants of the tensor-core engine (kernel parameter)
   bool tc_weights = false;
   int scene_views = 0;
-  int* d_counters = nullptr;   // [MAX_CHUNKS]
+  int* d_counters = nullptr;   // [MAX_CHUNKS] valid samples per shading batch
+  int* d_counters2 = nullptr;  // [MAX_CHUNKS] samples that needed a colour (tensor-core engine)
   int counters_used = 0;
   unsigned long long last_total = 0;
 
   DevBuf stage[4];             // host-sourced maps before packing
   DevBuf atlas[4];             // f64, f8, ftex, img (channel-last fp32)
   DevBuf atlas_fg;
-  DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in;
+  DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in, ws_lat, ws_list2;
   unsigned long long launches = 0;
   bool profiling = false;
   unsigned long long* d_timing = nullptr;   // [16] debug: per-stage wait cycles of the tensor-core row warps
@@ -109,9 +110,11 @@ extern "C" int kpn_create(int device, kpn_ctx** out) {
             cudaMalloc(&c->d_raw_target, sizeof(RawTarget)) == cudaSuccess &&
             cudaMalloc(&c->d_target, sizeof(DevTarget)) == cudaSuccess &&
             cudaMalloc(&c->d_wf32, sizeof(DevWeightsF32)) == cudaSuccess &&
-            cudaMalloc(&c->d_counters, sizeof(int) * MAX_CHUNKS) == cudaSuccess;
+            cudaMalloc(&c->d_counters, sizeof(int) * MAX_CHUNKS) == cudaSuccess &&
+            cudaMalloc(&c->d_counters2, sizeof(int) * MAX_CHUNKS) == cudaSuccess;
   if (!ok) { kpn_destroy(c); return KPN_ERR_CUDA; }
   cudaMemset(c->d_counters, 0, sizeof(int) * MAX_CHUNKS);
+  cudaMemset(c->d_counters2, 0, sizeof(int) * MAX_CHUNKS);
   *out = c;
   return KPN_OK;
 }
@@ -120,7 +123,7 @@ extern "C" void kpn_destroy(kpn_ctx* c) {
   if (!c) return;
   DeviceGuard g(c->device);
   cudaFree(c->d_raw_scene); cudaFree(c->d_scene); cudaFree(c->d_raw_target); cudaFree(c->d_target);
-  cudaFree(c->d_wf32); cudaFree(c->d_counters);
+  cudaFree(c->d_wf32); cudaFree(c->d_counters); cudaFree(c->d_counters2);
   c->wbuf.release();
   c->wblob.release();
   c->wlo.release();
@@ -129,6 +132,7 @@ extern "C" void kpn_destroy(kpn_ctx* c) {
   c->atlas_fg.release();
   c->ws_z.release(); c->ws_rgba.release(); c->ws_list.release(); c->ws_rayd.release(); c->ws_raynf.release();
   c->ws_contrib.release(); c->ws_zfine.release(); c->ws_out.release(); c->ws_in.release();
+  c->ws_lat.release(); c->ws_list2.release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   delete c;
 }
@@ -340,9 +344,14 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_
     c->ev_used += 2;
     KPN_CUDA(c, cudaEventRecord(e0, st));
   }
-  if (use_tc)
+  if (use_tc) {
+    KPN_CUDA(c, c->ws_lat.reserve((size_t)n * 48));
+    KPN_CUDA(c, c->ws_list2.reserve((size_t)n * 8));
     KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), engine == 2 ? nullptr : c->wlo.as<uint8_t>(), c->n_kpt,
-                                src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->num_sms, st, c->d_timing));
+                                src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->ws_lat.p, c->ws_list2.p,
+                                c->d_counters2 + slot, c->num_sms, st, c->d_timing));
+    c->launches++;
+  }
   else
     KPN_CUDA(c, launch_shade_simt(c->d_scene, c->d_wf32, src, c->ws_list.as<int>(), counter, n, query_mode, out5,
                                   c->num_sms, st));
@@ -353,6 +362,7 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_
 
 static int begin_counters(kpn_ctx* c, cudaStream_t st) {
   KPN_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(int) * MAX_CHUNKS, st));
+  KPN_CUDA(c, cudaMemsetAsync(c->d_counters2, 0, sizeof(int) * MAX_CHUNKS, st));
   c->counters_used = 0;
   c->last_total = 0;
   return KPN_OK;

@@ -1,24 +1,28 @@
 // Ray-march shading, engine 0: tcgen05 tensor-core MLPs with activations resident in tensor memory.
 //
-// One persistent CTA per SM, 9 warps:
-//   warps 0-3 : "row" warps of tile slot 0      warps 4-7 : row warps of tile slot 1
-//   warp 8    : TMEM allocator + TMA weight loader + the single thread that issues every tcgen05.mma
-// A tile is 128 rows = 4 warps x 32 lanes; a row is one (sample, source view) pair, the 3 views of a
-// sample sit in 3 adjacent lanes (10 samples per warp, 40 per tile), so every cross-view reduction of
-// the reference (view-weighted mean/variance pooling, src/utils.py:722-748; IBR blending weights, mean/var
-// and softmax, src/model.py:1286-1301) is a 3-lane shuffle.  Each row thread owns TMEM lane = its row:
-// it writes its layer inputs as packed fp16 straight into tensor memory (tcgen05.st), the MMA warp
-// multiplies them with the fp16 weights that stay resident in shared memory (loaded once per CTA with a
-// bulk TMA copy) into an fp32 accumulator in the other half of the slot's TMEM columns, and the row thread
-// reads its accumulator row back (tcgen05.ld), applies bias + activation in fp32 and overwrites it in
-// place with the next layer's fp16 input.  Activations never touch shared or global memory.  The two tile
-// slots ping-pong so the tensor pipe works on one tile while the CUDA cores run the other's epilogue.
-//
-// Stage table (A columns -> D columns inside the slot's 256 TMEM columns, R0 = [0,128), R1 = [128,256)):
-//   0 L0  190->128  A R0 D R1   1 L1 128->128 A R1 D R0   2 L2 136->120 A R0 D R1   3 L3 120->64 A R1 D R0
-//   4 P0|CMP 128->64|24 A R1 D R0   5 P1 64->64 A R0 D R1   (density head 64->2 stays fp32 on CUDA cores)
-//   6 BASE0 105->64 A R0 D R1   7 BASE1 64->32 A R1 D R0   8 VIS1A 32->32 A R0 D R1   9 VIS1B 32->33 A R1 D R0
-//   10 VIS2A 32->32 A R0 D R1   11 OUT0 37->16 A R1 D R0   (ray encoder, 32->1, 16->8->1 stay fp32 on CUDA cores)
+// Two persistent kernels per batch of valid samples (one CTA per SM each):
+//   shade_geo_kernel   : gather + keypoint encoding + geometry MLP (L0-L3) + view pooling + density tail (P0|compress, P1,
+//                        64->2 head).  Writes alpha/sdf per sample, the 24-wide compressed latent (fp16) to a scratch buffer,
+//                        and appends the samples that need a colour (density > 0; every valid sample in query mode) to a
+//                        second work list.  A sample with alpha == 0 has compositing weight exactly 0 (src/model.py:1167),
+//                        so skipping its colour is exact.
+//   shade_color_kernel : IBR colour head (BASE0, BASE1, VIS1A, VIS1B, VIS2A, OUT0 on tensor cores; ray encoder, 32->1,
+//                        16->8->1 in fp32 on CUDA cores) for the second list.
+// Common structure: 4 "row" warps per tile slot, a row = one (sample, source view) pair, the 3 views of a sample in 3
+// adjacent lanes (10 samples per warp, 40 per tile) so every cross-view reduction of the reference (view pooling,
+// src/utils.py:722-748; blending weights, mean/var, softmax, src/model.py:1286-1301) is a 3-lane shuffle.  Each row thread
+// owns TMEM lane = its row: it writes its layer input as packed fp16 straight into tensor memory (tcgen05.st), an issuer
+// thread multiplies it with fp16 weights resident in shared memory (bulk-TMA loaded once per CTA) into an fp32 accumulator in
+// the slot's other column region, tcgen05.commit -> mbarrier -> the row thread reads its accumulator row (tcgen05.ld), applies
+// bias + activation in fp32 and overwrites it in place with the next layer's fp16 input.  Activations never touch shared or
+// global memory.  Slots ping-pong so the tensor pipe works on one tile while the CUDA cores run another's epilogue:
+//   geo kernel  : 2 slots x 256 TMEM columns (regions R0/R1 of 128), + one W_lo issuer per slot (see "Precision" below);
+//   colour kernel: 3 slots x 128 TMEM columns (regions of 64).
+// Stage table (A region -> D region):
+//   geo   0 L0 190->128 R0->R1 | 1 L1 128->128 R1->R0 | 2 L2 136->120 R0->R1 | 3 L3 120->64 R1->R0
+//         4 P0|CMP 128->64|24 R1->R0 | 5 P1 64->64 R0->R1
+//   colour 6 BASE0 105->64 R0->R1 | 7 BASE1 64->32 R1->R0 | 8 VIS1A 32->32 R0->R1 | 9 VIS1B 32->33 R1->R0
+//         10 VIS2A 32->32 R0->R1 | 11 OUT0 37->16 R1->R0
 #include "kpn_device.cuh"
 #include "kpn_launch.h"
 #include "kpn_tc.cuh"
@@ -28,8 +32,11 @@ namespace kpn {
 namespace {
 
 constexpr int ROW_WARPS = 4;
-constexpr int NSLOT = 2;
+constexpr int NSLOT = 2;                                  // geo kernel tile slots
 constexpr int TC_THREADS = (NSLOT * ROW_WARPS + 3) * 32;  // 352: 8 row warps + hi issuer + one lo issuer per slot
+constexpr int CSLOT = 3;                                  // colour kernel tile slots
+constexpr int TCC_THREADS = (CSLOT * ROW_WARPS + 1) * 32; // 416: 12 row warps + issuer
+constexpr int GEO_NSTAGE = 6, COL_NSTAGE = 6;
 constexpr int SPW = 10;                                   // samples per warp (3 views each)
 constexpr int SPT = SPW * ROW_WARPS;                      // samples per tile
 constexpr float LOG2E = 1.4426950408889634f;
@@ -99,7 +106,7 @@ struct RowCtx {
   int gb;               // first lane of this row's 3-view group
   int l1, l2;           // the other two lanes of the group
   unsigned long long* tim;  // optional debug timing accumulators (only one recording thread per CTA slot 0)
-  int st;               // stage counter for the timing
+  int st, st0, st1;     // stage counter for the timing, cycling in [st0, st1)
 };
 
 __device__ __forceinline__ void signal_a(RowCtx& c) {
@@ -112,7 +119,7 @@ __device__ __forceinline__ void wait_acc(RowCtx& c) {
   tc::mbar_wait(c.acc_ready, c.ph);
   c.ph ^= 1u;
   tc::fence_after_sync();
-  if (c.tim) { atomicAdd(&c.tim[c.st], (unsigned long long)(clock64() - t0)); c.st = c.st + 1 == TC_NSTAGE ? 0 : c.st + 1; }
+  if (c.tim) { atomicAdd(&c.tim[c.st], (unsigned long long)(clock64() - t0)); c.st = c.st + 1 == c.st1 ? c.st0 : c.st + 1; }
 }
 __device__ __forceinline__ float gsum(const RowCtx& c, float x) {
   return x + __shfl_sync(FULL, x, c.l1) + __shfl_sync(FULL, x, c.l2);
@@ -159,9 +166,10 @@ __device__ __forceinline__ void encode_fast(const SceneS& S, int v, int k, const
 }
 
 template <int NK>
-__device__ __forceinline__ void row_tile(const SceneS& sc, const TcConsts& C, const SampleSrc& src,
+__device__ __forceinline__ void geo_tile(const SceneS& sc, const TcConsts& C, const SampleSrc& src,
                                          const int* __restrict__ list, int count, int tile, RowCtx& cx, int roww, int lane,
-                                         int query_mode, float* __restrict__ out5) {
+                                         int query_mode, float* __restrict__ out5, uint4* __restrict__ lat_out,
+                                         int2* __restrict__ list2, int* __restrict__ count2) {
   constexpr int ENC = 7 * NK;
   constexpr int A0C = tc_k0p(NK) / 2;
   const uint32_t R0 = cx.R0, R1 = cx.R1;
@@ -288,6 +296,57 @@ __device__ __forceinline__ void row_tile(const SceneS& sc, const TcConsts& C, co
       g0 = fmaf(C.w_p2[0][ch * 32 + i], h, g0);
       rad = fmaf(C.w_p2[1][ch * 32 + i], h, rad);
     }
+  }
+  // ---- outputs of the geometry pass: alpha / sdf (eval_func, src/model.py:978-997), the compressed latent for the colour
+  //      pass, and the colour work list (a sample with alpha == 0 composites with weight exactly 0: skipping it is exact)
+  {
+    const bool need = writer && (query_mode != 0 || rad > 0.0f);
+    if (writer) {
+      float* o = out5 + 5ll * id;
+      if (query_mode) { o[0] = g0; o[1] = rad; }
+      else { o[0] = fmaxf(rad, 0.0f); o[1] = g0; }
+      o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
+    }
+    const unsigned m = __ballot_sync(FULL, need);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      int pos = 0;
+      if (lane == leader) pos = atomicAdd(count2, __popc(m));
+      pos = __shfl_sync(FULL, pos, leader);
+      if (need) {
+        pos += __popc(m & ((1u << lane) - 1u));
+        list2[pos] = make_int2(pos, id);
+        uint4 w[3];
+        uint32_t* wp = reinterpret_cast<uint32_t*>(w);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) wp[i] = tc::pack_h2(lat[2 * i], lat[2 * i + 1]);
+        lat_out[3ll * pos + 0] = w[0]; lat_out[3ll * pos + 1] = w[1]; lat_out[3ll * pos + 2] = w[2];
+      }
+    }
+  }
+}
+
+// Colour pass for one tile of the second work list (entries: x = slot of the latent in the scratch buffer, y = sample id).
+__device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, const SampleSrc& src,
+                                           const int2* __restrict__ list2, int count, int tile, RowCtx& cx, int roww, int lane,
+                                           const uint4* __restrict__ lat_in, float* __restrict__ out5) {
+  const uint32_t R0 = cx.R0, R1 = cx.R1;
+  const int g = lane / 3;
+  const int v = lane - 3 * g;
+  const int si = tile * SPT + roww * SPW + min(g, SPW - 1);
+  const bool writer = (lane < 3 * SPW) && (v == 0) && (si < count);
+  const int2 ent = list2[min(si, count - 1)];
+  const int id = ent.y;
+  float p[3], d[3];
+  fetch_sample(src, id, p, d);
+  const Proj q = project_s(sc, v, p);
+  float lat[24];
+  {
+    uint4 w[3];
+    w[0] = __ldg(lat_in + 3ll * ent.x + 0); w[1] = __ldg(lat_in + 3ll * ent.x + 1); w[2] = __ldg(lat_in + 3ll * ent.x + 2);
+    const __half2* hp = reinterpret_cast<const __half2*>(w);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { float2 t2 = __half22float2(hp[i]); lat[2 * i] = t2.x; lat[2 * i + 1] = t2.y; }
   }
   // ---- colour branch inputs (src/model.py:806-832)
   float rgb[3], f[35], rd[4];
@@ -444,17 +503,15 @@ __device__ __forceinline__ void row_tile(const SceneS& sc, const TcConsts& C, co
     float r0 = gsum(cx, e * rgb[0]) * inv, r1 = gsum(cx, e * rgb[1]) * inv, r2 = gsum(cx, e * rgb[2]) * inv;
     if (writer) {
       float* o = out5 + 5ll * id;
-      if (query_mode) { o[0] = g0; o[1] = rad; }
-      else { o[0] = fmaxf(rad, 0.0f); o[1] = g0; }   // eval_func, src/model.py:978-997
       o[2] = r0; o[3] = r1; o[4] = r2;
     }
   }
 }
 
 // Precision: the geometry/density weights (stages 0..5) are applied as W = W_hi + W_lo, two fp16 terms.  W_hi stays
-// resident in shared memory; W_lo (the rounding residual of W_hi) is streamed from L2 through a small ring of 4 KB
-// slots with bulk TMA copies, one slot per 16-row K step, and accumulated into the same TMEM accumulator.  This removes
-// the weight-rounding error, which is systematic along a ray and dominated the RGB error of a plain fp16 pipeline
+// resident in shared memory; W_lo (the rounding residual of W_hi) is streamed from L2 through a ring of 4 KB slots with
+// bulk TMA copies, one slot per 16-row K step, and accumulated into the same TMEM accumulator.  This removes the
+// weight-rounding error, which is systematic along a ray and dominated the RGB error of a plain fp16 pipeline
 // (DESIGN.md "precision"); the tensor pipe has the headroom, the CUDA cores are the bottleneck.
 constexpr int TC_NLO = 6;          // stages with a W_lo pass
 constexpr uint32_t RING_SLOT = 4096;
@@ -462,8 +519,8 @@ constexpr uint32_t RING_SLOT = 4096;
 struct LoRing {
   uint32_t base;        // shared address of slot 0
   uint8_t* base_ptr;
-  uint64_t* full;       // [NRING] TMA -> MMA
-  uint64_t* empty;      // [NRING] MMA (tcgen05.commit) -> TMA
+  uint64_t* full;       // [n] TMA -> MMA
+  uint64_t* empty;      // [n] MMA (tcgen05.commit) -> TMA
   uint32_t full_par, empty_par;   // one parity bit per slot
   int head, n;
 };
@@ -475,7 +532,7 @@ __device__ __forceinline__ void ring_load(LoRing& rg, int r, const uint8_t* gsrc
   tc::bulk_g2s(rg.base_ptr + (size_t)r * RING_SLOT, gsrc, bytes, &rg.full[r]);
 }
 
-// Number of leading chunks of `stage` already requested by ring_prefetch().
+// Requests the leading chunks of `stage`; returns how many.
 __device__ __forceinline__ int ring_prefetch(LoRing& rg, const uint8_t* __restrict__ wlo, const TcPlan& plan, int stage) {
   const int Np = plan.st[stage].Np, nk = plan.st[stage].Kp / 16;
   const uint32_t bytes = 2u * (uint32_t)(Np / 8) * 128u;
@@ -485,9 +542,12 @@ __device__ __forceinline__ int ring_prefetch(LoRing& rg, const uint8_t* __restri
   return pf;
 }
 
+// which region holds the stage's A operand (bit = 1: R1); D goes to the other one.  Stages 1,3,4,7,9,11.
+constexpr uint32_t A_IN_R1 = 0xA9Au;
+
 __device__ __forceinline__ void issue_stage_lo(uint32_t slot_tm, LoRing& rg, const uint8_t* __restrict__ wlo, const TcPlan& plan,
                                                int stage, int pf) {
-  const uint32_t a_r1 = (0xA9Au >> stage) & 1u;
+  const uint32_t a_r1 = (A_IN_R1 >> stage) & 1u;
   const uint32_t a_tm = slot_tm + (a_r1 ? 128u : 0u), d_tm = slot_tm + (a_r1 ? 0u : 128u);
   const int Np = plan.st[stage].Np, nk = plan.st[stage].Kp / 16;
   const uint32_t lbo = (uint32_t)(Np / 8) * 128u, bytes = 2u * lbo;
@@ -505,14 +565,16 @@ __device__ __forceinline__ void issue_stage_lo(uint32_t slot_tm, LoRing& rg, con
   rg.head = (rg.head + nk) % rg.n;
 }
 
-__device__ __forceinline__ void issue_stage(uint32_t slot_tm, uint32_t wsmem, const TcPlan& plan, int stage) {
-  // which TMEM region holds the stage's A operand (1 = R1); D goes to the other one
-  const uint32_t a_r1 = (0xA9Au >> stage) & 1u;  // bits: stages 1,3,4,7,9,11
-  const uint32_t a_tm = slot_tm + (a_r1 ? 128u : 0u), d_tm = slot_tm + (a_r1 ? 0u : 128u);
+// MMAs of one stage on resident weights.  `region` = width of the slot's R0/R1 regions, `wbase` = shared address the
+// stage offsets of `plan` are relative to, minus `off0` (first stage resident in this kernel).
+__device__ __forceinline__ void issue_stage(uint32_t slot_tm, uint32_t region, uint32_t wsmem, uint32_t off0, const TcPlan& plan,
+                                            int stage) {
+  const uint32_t a_r1 = (A_IN_R1 >> stage) & 1u;
+  const uint32_t a_tm = slot_tm + (a_r1 ? region : 0u), d_tm = slot_tm + (a_r1 ? 0u : region);
   const int Kp = plan.st[stage].Kp, Np = plan.st[stage].Np;
   const uint32_t lbo = (uint32_t)(Np / 8) * 128u;
   const uint32_t idesc = tc::make_idesc_f16(128, Np);
-  const uint32_t b0 = wsmem + plan.st[stage].off;
+  const uint32_t b0 = wsmem + plan.st[stage].off - off0;
   for (int j = 0; j < Kp / 16; ++j) {
     uint64_t bd = tc::make_smem_desc(b0 + (uint32_t)j * 2u * lbo, lbo, 128u);
     tc::mma_ts(d_tm, a_tm + (uint32_t)j * 8u, bd, idesc, j > 0 ? 1u : 0u);
@@ -526,36 +588,51 @@ __device__ __forceinline__ void issue_stage(uint32_t slot_tm, uint32_t wsmem, co
   }
 }
 
+__device__ __forceinline__ void stage_scene(SceneS& scs, const DevScene& g, int NK, int t, int nthreads) {
+  for (int i = t; i < 3 * 12; i += nthreads) { scs.P[i / 12][i % 12] = g.P[i / 12][i % 12]; scs.E[i / 12][i % 12] = g.E[i / 12][i % 12]; }
+  for (int i = t; i < 3 * 3; i += nthreads) scs.C[i / 3][i % 3] = g.C[i / 3][i % 3];
+  for (int i = t; i < 3 * NK; i += nthreads)
+    scs.kc[i / NK][i % NK] = make_float4(g.kc[i / NK][i % NK][0], g.kc[i / NK][i % NK][1], g.kc[i / NK][i % NK][2], 0.0f);
+  if (t == 0) {
+    scs.wm1 = g.wm1; scs.hm1 = g.hm1; scs.znear = g.znear; scs.inv_zrange = 1.0f / (g.zfar - g.znear);
+    scs.sp_scale = g.sp_scale; scs.inv2sig2 = g.inv2sig2;
+    scs.f64 = g.f64; scs.f8 = g.f8; scs.ftex = g.ftex; scs.img = g.img;
+  }
+}
+
+__device__ __forceinline__ void load_weights(uint8_t* dst, const uint8_t* src, uint32_t bytes, uint64_t* wbar) {
+  tc::mbar_expect_tx(wbar, bytes);
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    tc::bulk_g2s(dst + off, src + off, n, wbar);
+  }
+  tc::mbar_wait(wbar, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// geometry + density kernel
+// ------------------------------------------------------------------------------------------------------------------
 template <int NK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
-                const uint8_t* __restrict__ wlo, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr, int query_mode,
-                float* __restrict__ out5, unsigned long long* __restrict__ timing) {
+shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
+                 const uint8_t* __restrict__ wlo, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
+                 int query_mode, float* __restrict__ out5, uint4* __restrict__ lat_out, int2* __restrict__ list2,
+                 int* __restrict__ count2, unsigned long long* __restrict__ timing) {
   extern __shared__ __align__(1024) uint8_t wsm[];
-  constexpr int NRING = NK <= 18 ? 6 : 2;   // TMA ring slots (4 KB each), split evenly between the two lo issuers
+  constexpr int NRING = NK <= 18 ? 12 : 10;   // TMA ring slots (4 KB each), split evenly between the two lo issuers
   // barriers: [0] weights | per slot s: [1+3s] a_ready (128 row threads), [2+3s] acc_ready (2 commits: hi issuer + lo issuer),
   //           [3+3s] hi_issued (hi issuer -> lo issuer: "the accumulator-initialising MMAs are in the pipe") | TMA ring full/empty
   __shared__ uint64_t bars[1 + 3 * NSLOT + 2 * NRING];
   __shared__ uint32_t tmem_base_s;
   __shared__ SceneS scs;
   constexpr TcPlan plan = make_tc_plan(NK);
+  constexpr uint32_t WBYTES = plan.st[GEO_NSTAGE].off;   // resident W_hi of stages 0..5
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int count = *count_ptr;
-  {
-    const DevScene& g = *scp;
-    for (int i = t; i < 3 * 12; i += TC_THREADS) { scs.P[i / 12][i % 12] = g.P[i / 12][i % 12]; scs.E[i / 12][i % 12] = g.E[i / 12][i % 12]; }
-    for (int i = t; i < 3 * 3; i += TC_THREADS) scs.C[i / 3][i % 3] = g.C[i / 3][i % 3];
-    for (int i = t; i < 3 * NK; i += TC_THREADS)
-      scs.kc[i / NK][i % NK] = make_float4(g.kc[i / NK][i % NK][0], g.kc[i / NK][i % NK][1], g.kc[i / NK][i % NK][2], 0.0f);
-    if (t == 0) {
-      scs.wm1 = g.wm1; scs.hm1 = g.hm1; scs.znear = g.znear; scs.inv_zrange = 1.0f / (g.zfar - g.znear);
-      scs.sp_scale = g.sp_scale; scs.inv2sig2 = g.inv2sig2;
-      scs.f64 = g.f64; scs.f8 = g.f8; scs.ftex = g.ftex; scs.img = g.img;
-    }
-  }
   const int ntiles = (count + SPT - 1) / SPT;
   uint64_t* wbar = &bars[0];
   const bool two_term = wlo != nullptr;
+  stage_scene(scs, *scp, NK, t, TC_THREADS);
 
   if (warp == 8) tc::tmem_alloc(&tmem_base_s, 512);
   if (t == 0) {
@@ -582,43 +659,37 @@ shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCons
   if (warp == 8) {
     // ---- hi issuer: resident W_hi tiles; initialises the accumulator of every stage
     if (lane == 0 && ntiles > 0) {
-      tc::mbar_expect_tx(wbar, plan.total_bytes);
-      for (uint32_t off = 0; off < plan.total_bytes; off += 32768u) {
-        uint32_t n = plan.total_bytes - off < 32768u ? plan.total_bytes - off : 32768u;
-        tc::bulk_g2s(wsm + off, wblob + off, n, wbar);
-      }
-      tc::mbar_wait(wbar, 0);
+      load_weights(wsm, wblob, WBYTES, wbar);
       const uint32_t wsmem = tc::smem_u32(wsm);
       int remaining[NSLOT], stage[NSLOT];
       uint32_t par[NSLOT];
-      for (int s = 0; s < NSLOT; ++s) { remaining[s] = tiles_of_slot(s) * TC_NSTAGE; stage[s] = 0; par[s] = 0; }
+      for (int s = 0; s < NSLOT; ++s) { remaining[s] = tiles_of_slot(s) * GEO_NSTAGE; stage[s] = 0; par[s] = 0; }
       while (remaining[0] > 0 || remaining[1] > 0) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
           if (remaining[s] > 0 && tc::mbar_test_wait(&bars[1 + 3 * s], par[s])) {
             tc::fence_after_sync();
-            issue_stage(tbase + (uint32_t)s * 256u, wsmem, plan, stage[s]);
-            const bool lo_follows = two_term && stage[s] < TC_NLO;
-            if (lo_follows) tc::mbar_arrive(&bars[3 + 3 * s]);      // lo issuer may now accumulate on top
+            issue_stage(tbase + (uint32_t)s * 256u, 128u, wsmem, 0u, plan, stage[s]);
+            if (two_term) tc::mbar_arrive(&bars[3 + 3 * s]);         // lo issuer may now accumulate on top
             else tc::mbar_arrive(&bars[2 + 3 * s]);                  // no lo pass: stand in for its commit
             tc::mma_commit(&bars[2 + 3 * s]);
             par[s] ^= 1u;
-            stage[s] = stage[s] + 1 == TC_NSTAGE ? 0 : stage[s] + 1;
+            stage[s] = stage[s] + 1 == GEO_NSTAGE ? 0 : stage[s] + 1;
             --remaining[s];
           }
         }
       }
     }
   } else if (warp == 9 || warp == 10) {
-    // ---- lo issuers (one per slot): stream the W_lo tiles of stages 0..5 from L2 through a private TMA ring.
-    // The chunks of the NEXT precise stage are requested as soon as the current one is committed (weights do not
-    // depend on the data), so their L2 latency hides behind the rows' epilogue.
+    // ---- lo issuers (one per slot): stream the W_lo tiles from L2 through a private TMA ring.  The chunks of the NEXT
+    // stage are requested as soon as the current one is committed (weights do not depend on the data), so their L2
+    // latency hides behind the rows' epilogue.
     const int s = warp - 9;
     const int my_tiles = tiles_of_slot(s);
     if (lane == 0 && my_tiles > 0 && two_term) {
       constexpr int NR = NRING / NSLOT;
       LoRing rg;
-      rg.base_ptr = wsm + plan.total_bytes + (size_t)s * NR * RING_SLOT;
+      rg.base_ptr = wsm + WBYTES + (size_t)s * NR * RING_SLOT;
       rg.base = tc::smem_u32(rg.base_ptr);
       rg.full = &bars[1 + 3 * NSLOT + s * NR];
       rg.empty = &bars[1 + 3 * NSLOT + NRING + s * NR];
@@ -649,10 +720,10 @@ shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCons
     cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
     cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
     cx.tim = (timing != nullptr && warp == 0 && lane == 0) ? timing : nullptr;
-    cx.st = 0;
+    cx.st = 0; cx.st0 = 0; cx.st1 = GEO_NSTAGE;
     for (int tile = blockIdx.x * NSLOT + slot; tile < ntiles; tile += gridDim.x * NSLOT) {
       long long t0 = cx.tim ? clock64() : 0;
-      row_tile<NK>(scs, C, src, list, count, tile, cx, roww, lane, query_mode, out5);
+      geo_tile<NK>(scs, C, src, list, count, tile, cx, roww, lane, query_mode, out5, lat_out, list2, count2);
       if (cx.tim) { atomicAdd(&cx.tim[12], (unsigned long long)(clock64() - t0)); atomicAdd(&cx.tim[13], 1ull); }
     }
   }
@@ -661,38 +732,128 @@ shade_tc_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCons
   if (warp == 8) tc::tmem_dealloc(tbase, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// colour kernel
+// ------------------------------------------------------------------------------------------------------------------
+template <int NK>
+__global__ void __launch_bounds__(TCC_THREADS, 1)
+shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
+                   SampleSrc src, const int2* __restrict__ list2, const int* __restrict__ count_ptr,
+                   const uint4* __restrict__ lat_in, float* __restrict__ out5, unsigned long long* __restrict__ timing) {
+  extern __shared__ __align__(1024) uint8_t wsm[];
+  __shared__ uint64_t bars[1 + 2 * CSLOT];   // [0] weights | per slot: a_ready, acc_ready
+  __shared__ uint32_t tmem_base_s;
+  __shared__ SceneS scs;
+  constexpr TcPlan plan = make_tc_plan(NK);
+  constexpr uint32_t OFF0 = plan.st[GEO_NSTAGE].off, WBYTES = plan.total_bytes - plan.st[GEO_NSTAGE].off;
+  constexpr int ISSUER = CSLOT * ROW_WARPS;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int count = *count_ptr;
+  const int ntiles = (count + SPT - 1) / SPT;
+  stage_scene(scs, *scp, NK, t, TCC_THREADS);
+  if (warp == ISSUER) tc::tmem_alloc(&tmem_base_s, 512);
+  if (t == 0) {
+    tc::mbar_init(&bars[0], 1);
+    for (int s = 0; s < CSLOT; ++s) { tc::mbar_init(&bars[1 + 2 * s], ROW_WARPS * 32); tc::mbar_init(&bars[2 + 2 * s], 1); }
+    tc::fence_mbar_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  auto tiles_of_slot = [&](int s) {
+    int n = 0;
+    for (int tile = blockIdx.x * CSLOT + s; tile < ntiles; tile += gridDim.x * CSLOT) ++n;
+    return n;
+  };
+  if (warp == ISSUER) {
+    if (lane == 0 && ntiles > 0) {
+      load_weights(wsm, wblob + OFF0, WBYTES, &bars[0]);
+      const uint32_t wsmem = tc::smem_u32(wsm);
+      int remaining[CSLOT], stage[CSLOT], left = 0;
+      uint32_t par[CSLOT];
+      for (int s = 0; s < CSLOT; ++s) { remaining[s] = tiles_of_slot(s) * COL_NSTAGE; stage[s] = 0; par[s] = 0; left += remaining[s]; }
+      while (left > 0) {
+#pragma unroll
+        for (int s = 0; s < CSLOT; ++s) {
+          if (remaining[s] > 0 && tc::mbar_test_wait(&bars[1 + 2 * s], par[s])) {
+            tc::fence_after_sync();
+            issue_stage(tbase + (uint32_t)s * 128u, 64u, wsmem, OFF0, plan, GEO_NSTAGE + stage[s]);
+            tc::mma_commit(&bars[2 + 2 * s]);
+            par[s] ^= 1u;
+            stage[s] = stage[s] + 1 == COL_NSTAGE ? 0 : stage[s] + 1;
+            --remaining[s];
+            --left;
+          }
+        }
+      }
+    }
+  } else {
+    const int slot = warp / ROW_WARPS, roww = warp % ROW_WARPS;
+    RowCtx cx;
+    const uint32_t tm = tbase + (uint32_t)slot * 128u + ((uint32_t)(roww * 32) << 16);
+    cx.R0 = tm; cx.R1 = tm + 64u;
+    cx.a_ready = &bars[1 + 2 * slot];
+    cx.acc_ready = &bars[2 + 2 * slot];
+    cx.ph = 0;
+    cx.gb = 3 * (lane / 3);
+    cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
+    cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
+    cx.tim = (timing != nullptr && warp == 0 && lane == 0) ? timing : nullptr;
+    cx.st = GEO_NSTAGE; cx.st0 = GEO_NSTAGE; cx.st1 = GEO_NSTAGE + COL_NSTAGE;
+    for (int tile = blockIdx.x * CSLOT + slot; tile < ntiles; tile += gridDim.x * CSLOT) {
+      long long t0 = cx.tim ? clock64() : 0;
+      color_tile(scs, C, src, list2, count, tile, cx, roww, lane, lat_in, out5);
+      if (cx.tim) { atomicAdd(&cx.tim[14], (unsigned long long)(clock64() - t0)); atomicAdd(&cx.tim[15], 1ull); }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == ISSUER) tc::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace
 
 size_t tc_weight_blob_bytes(int n_kpt) { return make_tc_plan(n_kpt).total_bytes; }
 size_t tc_weight_lo_bytes(int n_kpt) { return make_tc_plan(n_kpt).st[TC_NLO].off; }
 bool tc_supported(int n_views, int n_kpt, int sp_level) { return n_views == 3 && (n_kpt == 18 || n_kpt == 24) && sp_level == 3; }
 
-cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wlo, int n_kpt, const SampleSrc& src,
-                            const int* list, const int* counter, long long n_max, int query_mode, float* out5, int num_sms,
-                            cudaStream_t st, unsigned long long* timing) {
-  const size_t smem = tc_weight_blob_bytes(n_kpt) + (size_t)(n_kpt <= 18 ? 6 : 2) * RING_SLOT;
-  long long max_tiles = (n_max + SPT - 1) / SPT;
+template <int NK>
+static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wlo, const SampleSrc& src,
+                                  const int* list, const int* counter, long long n_max, int query_mode, float* out5, uint4* lat,
+                                  int2* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
+  constexpr TcPlan plan = make_tc_plan(NK);
+  const size_t smem_geo = plan.st[GEO_NSTAGE].off + (size_t)(NK <= 18 ? 12 : 10) * RING_SLOT;
+  const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(shade_geo_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_geo);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(shade_color_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const long long max_tiles = (n_max + SPT - 1) / SPT;
   long long g = (max_tiles + NSLOT - 1) / NSLOT;
   int grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
-  cudaError_t e;
-  if (n_kpt == 18) {
-    static bool attr18 = false;
-    if (!attr18) {
-      e = cudaFuncSetAttribute(shade_tc_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr18 = true;
-    }
-    shade_tc_kernel<18><<<grid, TC_THREADS, smem, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5, timing);
-  } else {
-    static bool attr24 = false;
-    if (!attr24) {
-      e = cudaFuncSetAttribute(shade_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr24 = true;
-    }
-    shade_tc_kernel<24><<<grid, TC_THREADS, smem, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5, timing);
-  }
+  shade_geo_kernel<NK><<<grid, TC_THREADS, smem_geo, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5, lat, list2, count2,
+                                                          timing);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  g = (max_tiles + CSLOT - 1) / CSLOT;
+  grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
+  shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, count2, lat, out5, timing);
   return cudaGetLastError();
+}
+
+cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wlo, int n_kpt, const SampleSrc& src,
+                            const int* list, const int* counter, long long n_max, int query_mode, float* out5, void* lat_scratch,
+                            void* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
+  if (n_kpt == 18)
+    return launch_tc_impl<18>(sc, C, wblob, wlo, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch, (int2*)list2, count2,
+                              num_sms, st, timing);
+  return launch_tc_impl<24>(sc, C, wblob, wlo, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch, (int2*)list2, count2,
+                            num_sms, st, timing);
 }
 
 }  // namespace kpn
