@@ -177,6 +177,8 @@ int kpn_set_profiling(kpn_ctx* ctx, int enable);
 /* Unit test hook for the tensor-core primitive (tests/test_gpu_umma.py): D(128,N) fp32 = A(128,K) fp16 * B(N,K)^T fp16
  * on one CTA through tcgen05.mma.  Device pointers.  variant bit0: B core-matrix arrangement, bit1: A from shared memory. */
 int kpn_selftest_umma(int N, int K, const void* A, const void* B, float* D, int variant, void* stream);
+/* Same for the CTA-pair form (cta_group::2): D(256,N) = A(256,K) * B(N,K)^T on a 2-CTA cluster. */
+int kpn_selftest_umma2(int N, int K, const void* A, const void* B, float* D, void* stream);
 
 #ifdef __cplusplus
 }

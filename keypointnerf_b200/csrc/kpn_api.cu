@@ -57,7 +57,7 @@ struct kpn_ctx {
   DevWeightsF32* d_wf32 = nullptr;
   DevBuf wbuf;
   DevBuf wblob;                // fp16 weight tiles of the tensor-core engine (core-matrix layout)
-  DevBuf wlo;                  // fp16 rounding residuals of the geometry/density weight tiles (streamed from L2)
+  DevBuf wlo;                  // per-CTA-rank half-blobs [W_hi halves | W_lo halves] of the geometry stages (CTA-pair kernel)
   TcConsts tcc;                // fp32 constants of the tensor-core engine (kernel parameter)
   bool tc_weights = false;
   int scene_views = 0;
@@ -205,8 +205,8 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
   if (tc_supported(3, w->n_kpt, w->sp_level)) {
     const TcPlan plan = make_tc_plan(w->n_kpt);
     std::vector<__half> blob(plan.total_bytes / 2, __float2half_rn(0.0f));
-    const size_t lo_bytes = tc_weight_lo_bytes(w->n_kpt);
-    std::vector<__half> blob_lo(lo_bytes / 2, __float2half_rn(0.0f));
+    const size_t geo_bytes = tc_weight_lo_bytes(w->n_kpt);          // bytes of the full W_hi tiles of stages 0..5
+    std::vector<__half> pair(tc_pair_blob_bytes(w->n_kpt) / 2, __float2half_rn(0.0f));   // [rank][hi halves | lo halves]
     // stage -> (layer, first row in the tile); stage 4 stacks the density layer 0 and the colour compress layer
     const int stage_layer[TC_NSTAGE] = {L_GEO0, L_GEO1, L_GEO2, L_GEO3, L_DEN0, L_DEN1, L_BASE0, L_BASE1, L_VIS1A, L_VIS1B, L_VIS2A, L_OUT0};
     auto put = [&](int stage, int layer, int row0) {
@@ -219,15 +219,20 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
           const float wv = We[layer][(size_t)o * L.n_in + i];
           const __half hi = __float2half_rn(wv);
           blob[at] = hi;
-          if (at < blob_lo.size()) blob_lo[at] = __float2half_rn(wv - __half2float(hi));
+          if (stage < 6) {   // geometry stages: row n of the tile goes to CTA rank n / (Np/2), as row n % (Np/2) of its half tile
+            const int n = row0 + o, Nh = Np / 2, rk = n / Nh;
+            const size_t half_at = ((size_t)rk * geo_bytes + plan.st[stage].off / 2 + tc::core_offset_bytes(n % Nh, i, Nh)) / 2;
+            pair[half_at] = hi;
+            pair[half_at + geo_bytes / 4] = __float2half_rn(wv - __half2float(hi));   // lo halves follow the hi halves
+          }
         }
     };
     for (int sidx = 0; sidx < TC_NSTAGE; ++sidx) put(sidx, stage_layer[sidx], 0);
     put(4, L_CMP, 64);
     KPN_CUDA(c, c->wblob.reserve(plan.total_bytes));
     KPN_CUDA(c, cudaMemcpy(c->wblob.p, blob.data(), plan.total_bytes, cudaMemcpyHostToDevice));
-    KPN_CUDA(c, c->wlo.reserve(lo_bytes));
-    KPN_CUDA(c, cudaMemcpy(c->wlo.p, blob_lo.data(), lo_bytes, cudaMemcpyHostToDevice));
+    KPN_CUDA(c, c->wlo.reserve(pair.size() * 2));
+    KPN_CUDA(c, cudaMemcpy(c->wlo.p, pair.data(), pair.size() * 2, cudaMemcpyHostToDevice));
     TcConsts& T = c->tcc;
     memset(&T, 0, sizeof(T));
     auto bias = [&](int layer, float* dst) { for (int o = 0; o < w->layer[layer].n_out; ++o) dst[o] = w->layer[layer].bias[o]; };
@@ -347,7 +352,7 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_
   if (use_tc) {
     KPN_CUDA(c, c->ws_lat.reserve((size_t)n * 48));
     KPN_CUDA(c, c->ws_list2.reserve((size_t)n * 8));
-    KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), engine == 2 ? nullptr : c->wlo.as<uint8_t>(), c->n_kpt,
+    KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), c->wlo.as<uint8_t>(), engine == 2 ? 0 : 1, c->n_kpt,
                                 src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->ws_lat.p, c->ws_list2.p,
                                 c->d_counters2 + slot, c->num_sms, st, c->d_timing));
     c->launches++;

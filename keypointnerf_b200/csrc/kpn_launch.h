@@ -18,11 +18,14 @@ cudaError_t launch_shade_simt(const DevScene* sc, const DevWeightsF32* W, const 
 cudaError_t launch_composite(const float* rgba, const float* z, int r0, int nr, int S, long long plane, float* color,
                              float* depth, float* alpha, float* sdf, float* contrib, cudaStream_t st);
 cudaError_t launch_importance(const float* contrib, const float* z, int nr, int Sc, int Sf, float* zout, cudaStream_t st);
-// Tensor-core engine: geometry+density kernel, then the colour kernel on the samples with density > 0.
-// lat_scratch: n_max x 48 bytes, list2: n_max x int2, count2: device int (zeroed by the caller).
-cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wlo, int n_kpt, const SampleSrc& src,
-                            const int* list, const int* counter, long long n_max, int query_mode, float* out5, void* lat_scratch,
-                            void* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing = nullptr);
+// Tensor-core engine: geometry+density kernel (CTA pairs), then the colour kernel on the samples with density > 0.
+// wblob: full fp16 W_hi tiles (colour stages are read from it); wpair: per-CTA-rank half-blobs [W_hi halves | W_lo halves] of the
+// geometry stages; lat_scratch: n_max x 48 bytes, list2: n_max x int2, count2: device int (zeroed by the caller).
+cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term, int n_kpt,
+                            const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
+                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st,
+                            unsigned long long* timing = nullptr);
+size_t tc_pair_blob_bytes(int n_kpt);
 size_t tc_weight_blob_bytes(int n_kpt);
 size_t tc_weight_lo_bytes(int n_kpt);
 bool tc_supported(int n_views, int n_kpt, int sp_level);

@@ -86,7 +86,77 @@ umma_selftest_kernel(int N, int K, const __half* __restrict__ A, const __half* _
   if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
+// 2-CTA variant: D[256][N] = A[256][K] * B[N][K]^T.  CTA r holds rows 128r..128r+127 of A (TMEM) and rows
+// r*N/2 .. (r+1)*N/2-1 of B (shared memory, [k/8][n/8] core-matrix order with N/2 rows).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma2_selftest_kernel(int N, int K, const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar_a, bar_acc;
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int Nh = N / 2;
+  if (warp == 0) tc::tmem_alloc2(&tmem_base_s, 512);
+  if (t == 0) { tc::mbar_init(&bar_a, 256); tc::mbar_init(&bar_acc, 1); tc::fence_mbar_init(); }
+  for (int idx = t; idx < Nh * K; idx += 128) {
+    int n = idx / K, k = idx % K;
+    *reinterpret_cast<__half*>(smem + tc::core_offset_bytes(n, k, Nh)) = B[(size_t)(rank * Nh + n) * K + k];
+  }
+  tc::fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync_all();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+  const uint32_t a_col = 0, d_col = 256;
+  const __half* arow = A + (size_t)(rank * 128 + t) * K;
+  for (int kc = 0; kc < K / 16; ++kc) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = tc::pack_h2(__half2float(arow[kc * 16 + 2 * i]), __half2float(arow[kc * 16 + 2 * i + 1]));
+    tc::tmem_st8(lane_base + a_col + kc * 8, r);
+  }
+  tc::wait_st();
+  tc::fence_before_sync();
+  tc::mbar_arrive_cluster(&bar_a, 0);   // every row thread of both CTAs arrives on the LEADER's barrier
+  if (rank == 0 && t == 0) {
+    tc::mbar_wait(&bar_a, 0);
+    tc::fence_after_sync();
+    const uint32_t idesc = tc::make_idesc_f16(256, N);
+    const uint32_t lbo = (uint32_t)(Nh / 8) * 128u;
+    for (int j = 0; j < K / 16; ++j) {
+      uint64_t bd = tc::make_smem_desc(tc::smem_u32(smem) + j * 2 * lbo, lbo, 128u);
+      tc::mma_ts2(tbase + d_col, tbase + a_col + j * 8, bd, idesc, j > 0);
+    }
+    tc::mma_commit2(&bar_acc);
+  }
+  tc::mbar_wait(&bar_acc, 0);
+  tc::fence_after_sync();
+  for (int c = 0; c < N; c += 8) {
+    uint32_t r[8];
+    tc::tmem_ld8(lane_base + d_col + c, r);
+    tc::wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) D[(size_t)(rank * 128 + t) * N + c + i] = __uint_as_float(r[i]);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync_all();
+  if (warp == 0) tc::tmem_dealloc2(tbase, 512);
+}
+
 }  // namespace kpn
+
+// 2-CTA self-test: A (256,K) fp16, B (N,K) fp16, D (256,N) fp32: device pointers.  N % 32 == 0.
+extern "C" int kpn_selftest_umma2(int N, int K, const void* A, const void* B, float* D, void* stream) {
+  if (N % 32 || N < 32 || N > 256 || K % 16 || K < 16 || K > 256) return -1;
+  size_t smem = (size_t)(N / 2) * K * 2;
+  cudaError_t e = cudaFuncSetAttribute(kpn::umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -2;
+  kpn::umma2_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(N, K, (const __half*)A, (const __half*)B, D);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
 
 // A (128,K) fp16, B (N,K) fp16, D (128,N) fp32: device pointers.  N % 16 == 0, 16 <= N <= 256, K % 16 == 0.
 extern "C" int kpn_selftest_umma(int N, int K, const void* A, const void* B, float* D, int variant, void* stream) {

@@ -33,7 +33,7 @@ namespace {
 
 constexpr int ROW_WARPS = 4;
 constexpr int NSLOT = 2;                                  // geo kernel tile slots
-constexpr int TC_THREADS = (NSLOT * ROW_WARPS + 3) * 32;  // 352: 8 row warps + hi issuer + one lo issuer per slot
+constexpr int TC_THREADS = (NSLOT * ROW_WARPS + 1) * 32;  // 288: 8 row warps + allocator/issuer warp
 constexpr int CSLOT = 3;                                  // colour kernel tile slots
 constexpr int TCC_THREADS = (CSLOT * ROW_WARPS + 1) * 32; // 416: 12 row warps + issuer
 constexpr int GEO_NSTAGE = 6, COL_NSTAGE = 6;
@@ -101,6 +101,7 @@ __device__ __forceinline__ float boundary_weight_fast(const Proj& q) {
 struct RowCtx {
   uint32_t R0, R1;      // TMEM addresses (lane field already set) of the slot's two column regions
   uint64_t* a_ready;    // row threads -> MMA thread : "layer input is in TMEM"   (count 128)
+  uint32_t a_ready_cl;  // != 0: cluster-mapped shared address of the LEADER CTA's a_ready (CTA-pair kernel, count 256)
   uint64_t* acc_ready;  // MMA thread -> row threads : "accumulator is complete"  (tcgen05.commit)
   uint32_t ph;          // parity of acc_ready this thread waits on next
   int gb;               // first lane of this row's 3-view group
@@ -112,7 +113,8 @@ struct RowCtx {
 __device__ __forceinline__ void signal_a(RowCtx& c) {
   tc::wait_st();
   tc::fence_before_sync();
-  tc::mbar_arrive(c.a_ready);
+  if (c.a_ready_cl) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(c.a_ready_cl) : "memory");
+  else tc::mbar_arrive(c.a_ready);
 }
 __device__ __forceinline__ void wait_acc(RowCtx& c) {
   long long t0 = c.tim ? clock64() : 0;
@@ -508,61 +510,35 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
   }
 }
 
-// Precision: the geometry/density weights (stages 0..5) are applied as W = W_hi + W_lo, two fp16 terms.  W_hi stays
-// resident in shared memory; W_lo (the rounding residual of W_hi) is streamed from L2 through a ring of 4 KB slots with
-// bulk TMA copies, one slot per 16-row K step, and accumulated into the same TMEM accumulator.  This removes the
-// weight-rounding error, which is systematic along a ray and dominated the RGB error of a plain fp16 pipeline
-// (DESIGN.md "precision"); the tensor pipe has the headroom, the CUDA cores are the bottleneck.
+// Precision: the geometry/density weights (stages 0..5) are applied as W = W_hi + W_lo, two fp16 terms accumulated into
+// the same TMEM accumulator.  This removes the weight-rounding error, which is systematic along a ray and dominated the RGB
+// error of a plain fp16 pipeline (DESIGN.md "precision"); the tensor pipe has the headroom, the CUDA cores are the bottleneck.
+// Shared memory cannot hold two copies of the weights in one CTA, so the geometry kernel runs as CTA PAIRS (cta_group::2):
+// each CTA of a 2-CTA cluster keeps HALF of the output rows of every W_hi and W_lo tile resident, the pair's leader issues
+// M=256 MMAs that cover one tile of each CTA.
 constexpr int TC_NLO = 6;          // stages with a W_lo pass
-constexpr uint32_t RING_SLOT = 4096;
-
-struct LoRing {
-  uint32_t base;        // shared address of slot 0
-  uint8_t* base_ptr;
-  uint64_t* full;       // [n] TMA -> MMA
-  uint64_t* empty;      // [n] MMA (tcgen05.commit) -> TMA
-  uint32_t full_par, empty_par;   // one parity bit per slot
-  int head, n;
-};
-
-__device__ __forceinline__ void ring_load(LoRing& rg, int r, const uint8_t* gsrc, uint32_t bytes) {
-  tc::mbar_wait(&rg.empty[r], ((rg.empty_par >> r) & 1u) ^ 1u);   // slot free (passes immediately the first time)
-  rg.empty_par ^= 1u << r;
-  tc::mbar_expect_tx(&rg.full[r], bytes);
-  tc::bulk_g2s(rg.base_ptr + (size_t)r * RING_SLOT, gsrc, bytes, &rg.full[r]);
-}
-
-// Requests the leading chunks of `stage`; returns how many.
-__device__ __forceinline__ int ring_prefetch(LoRing& rg, const uint8_t* __restrict__ wlo, const TcPlan& plan, int stage) {
-  const int Np = plan.st[stage].Np, nk = plan.st[stage].Kp / 16;
-  const uint32_t bytes = 2u * (uint32_t)(Np / 8) * 128u;
-  const uint8_t* src = wlo + plan.st[stage].off;
-  const int pf = nk < rg.n ? nk : rg.n;
-  for (int j = 0; j < pf; ++j) ring_load(rg, (rg.head + j) % rg.n, src + (size_t)j * bytes, bytes);
-  return pf;
-}
 
 // which region holds the stage's A operand (bit = 1: R1); D goes to the other one.  Stages 1,3,4,7,9,11.
 constexpr uint32_t A_IN_R1 = 0xA9Au;
 
-__device__ __forceinline__ void issue_stage_lo(uint32_t slot_tm, LoRing& rg, const uint8_t* __restrict__ wlo, const TcPlan& plan,
-                                               int stage, int pf) {
+// CTA-pair MMAs of one geometry stage.  `wsmem`: shared address of this CTA's half-blob = [W_hi halves of stages 0..5 |
+// W_lo halves of stages 0..5]; a stage's half tile sits at plan offset / 2.
+__device__ __forceinline__ void issue_stage_pair(uint32_t slot_tm, uint32_t wsmem, uint32_t lo_base, const TcPlan& plan, int stage,
+                                                 bool two_term) {
   const uint32_t a_r1 = (A_IN_R1 >> stage) & 1u;
   const uint32_t a_tm = slot_tm + (a_r1 ? 128u : 0u), d_tm = slot_tm + (a_r1 ? 0u : 128u);
-  const int Np = plan.st[stage].Np, nk = plan.st[stage].Kp / 16;
-  const uint32_t lbo = (uint32_t)(Np / 8) * 128u, bytes = 2u * lbo;
-  const uint32_t idesc = tc::make_idesc_f16(128, Np);
-  const uint8_t* src = wlo + plan.st[stage].off;
-  for (int j = 0; j < nk; ++j) {
-    const int r = (rg.head + j) % rg.n;
-    tc::mbar_wait(&rg.full[r], (rg.full_par >> r) & 1u);
-    rg.full_par ^= 1u << r;
-    uint64_t bd = tc::make_smem_desc(rg.base + (uint32_t)r * RING_SLOT, lbo, 128u);
-    tc::mma_ts(d_tm, a_tm + (uint32_t)j * 8u, bd, idesc, 1u);
-    tc::mma_commit(&rg.empty[r]);
-    if (j + pf < nk) ring_load(rg, (rg.head + j + pf) % rg.n, src + (size_t)(j + pf) * bytes, bytes);
-  }
-  rg.head = (rg.head + nk) % rg.n;
+  const int Kp = plan.st[stage].Kp, Np = plan.st[stage].Np;
+  const uint32_t lbo = (uint32_t)(Np / 16) * 128u;       // half tile: Np/2 rows -> (Np/2)/8 core matrices per K chunk
+  const uint32_t idesc = tc::make_idesc_f16(256, Np);
+  const uint32_t b_hi = wsmem + plan.st[stage].off / 2u, b_lo = b_hi + lo_base;
+  for (int j = 0; j < Kp / 16; ++j)
+    tc::mma_ts2(d_tm, a_tm + (uint32_t)j * 8u, tc::make_smem_desc(b_hi + (uint32_t)j * 2u * lbo, lbo, 128u), idesc, j > 0 ? 1u : 0u);
+  if (stage == 4 || stage == 5)   // density tail: activations come as hi | lo, the lo half sits Kp/2 columns further
+    for (int j = 0; j < Kp / 16; ++j)
+      tc::mma_ts2(d_tm, a_tm + (uint32_t)(Kp / 2) + (uint32_t)j * 8u, tc::make_smem_desc(b_hi + (uint32_t)j * 2u * lbo, lbo, 128u), idesc, 1u);
+  if (two_term)
+    for (int j = 0; j < Kp / 16; ++j)
+      tc::mma_ts2(d_tm, a_tm + (uint32_t)j * 8u, tc::make_smem_desc(b_lo + (uint32_t)j * 2u * lbo, lbo, 128u), idesc, 1u);
 }
 
 // MMAs of one stage on resident weights.  `region` = width of the slot's R0/R1 regions, `wbase` = shared address the
@@ -610,69 +586,62 @@ __device__ __forceinline__ void load_weights(uint8_t* dst, const uint8_t* src, u
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// geometry + density kernel
+// geometry + density kernel (CTA pairs)
 // ------------------------------------------------------------------------------------------------------------------
 template <int NK>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
-                 const uint8_t* __restrict__ wlo, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
+                 int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
                  int query_mode, float* __restrict__ out5, uint4* __restrict__ lat_out, int2* __restrict__ list2,
                  int* __restrict__ count2, unsigned long long* __restrict__ timing) {
   extern __shared__ __align__(1024) uint8_t wsm[];
-  constexpr int NRING = NK <= 18 ? 12 : 10;   // TMA ring slots (4 KB each), split evenly between the two lo issuers
-  // barriers: [0] weights | per slot s: [1+3s] a_ready (128 row threads), [2+3s] acc_ready (2 commits: hi issuer + lo issuer),
-  //           [3+3s] hi_issued (hi issuer -> lo issuer: "the accumulator-initialising MMAs are in the pipe") | TMA ring full/empty
-  __shared__ uint64_t bars[1 + 3 * NSLOT + 2 * NRING];
+  // barriers: [0] weights | per slot s: [1+2s] a_ready (256 row threads of the pair; only the leader's copy is used),
+  //           [2+2s] acc_ready (one multicast commit per stage, each CTA waits on its own copy)
+  __shared__ uint64_t bars[1 + 2 * NSLOT];
   __shared__ uint32_t tmem_base_s;
   __shared__ SceneS scs;
   constexpr TcPlan plan = make_tc_plan(NK);
-  constexpr uint32_t WBYTES = plan.st[GEO_NSTAGE].off;   // resident W_hi of stages 0..5
+  constexpr uint32_t WBYTES = plan.st[GEO_NSTAGE].off;   // per CTA: half of W_hi + half of W_lo of stages 0..5
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int count = *count_ptr;
   const int ntiles = (count + SPT - 1) / SPT;
-  uint64_t* wbar = &bars[0];
-  const bool two_term = wlo != nullptr;
   stage_scene(scs, *scp, NK, t, TC_THREADS);
 
-  if (warp == 8) tc::tmem_alloc(&tmem_base_s, 512);
+  if (warp == 8) tc::tmem_alloc2(&tmem_base_s, 512);
   if (t == 0) {
-    tc::mbar_init(wbar, 1);
-    for (int s = 0; s < NSLOT; ++s) {
-      tc::mbar_init(&bars[1 + 3 * s], ROW_WARPS * 32);
-      tc::mbar_init(&bars[2 + 3 * s], 2);
-      tc::mbar_init(&bars[3 + 3 * s], 1);
-    }
-    for (int r = 0; r < 2 * NRING; ++r) tc::mbar_init(&bars[1 + 3 * NSLOT + r], 1);
+    tc::mbar_init(&bars[0], 1);
+    for (int s = 0; s < NSLOT; ++s) { tc::mbar_init(&bars[1 + 2 * s], 2 * ROW_WARPS * 32); tc::mbar_init(&bars[2 + 2 * s], 1); }
     tc::fence_mbar_init();
   }
+  __syncthreads();
+  if (warp == 8 && lane == 0) load_weights(wsm, wpair + (size_t)rank * WBYTES, WBYTES, &bars[0]);   // this CTA's half-blob
   tc::fence_before_sync();
   __syncthreads();
+  tc::cluster_sync_all();     // both CTAs: barriers initialised, TMEM allocated, weights resident
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
-  // tiles of this CTA: slot s takes tile (i*gridDim.x + blockIdx.x)*NSLOT + s
-  auto tiles_of_slot = [&](int s) {
+  // pair iteration i of slot s covers tiles 2*P and 2*P+1 with P = (i*ncl + cl)*NSLOT + s; this CTA takes tile 2*P + rank
+  auto iters_of_slot = [&](int s) {
     int n = 0;
-    for (int tile = blockIdx.x * NSLOT + s; tile < ntiles; tile += gridDim.x * NSLOT) ++n;
+    for (int P = cl * NSLOT + s; 2 * P < ntiles; P += ncl * NSLOT) ++n;
     return n;
   };
 
   if (warp == 8) {
-    // ---- hi issuer: resident W_hi tiles; initialises the accumulator of every stage
-    if (lane == 0 && ntiles > 0) {
-      load_weights(wsm, wblob, WBYTES, wbar);
+    if (lane == 0 && rank == 0 && ntiles > 0) {   // the pair's single MMA issuer
       const uint32_t wsmem = tc::smem_u32(wsm);
       int remaining[NSLOT], stage[NSLOT];
       uint32_t par[NSLOT];
-      for (int s = 0; s < NSLOT; ++s) { remaining[s] = tiles_of_slot(s) * GEO_NSTAGE; stage[s] = 0; par[s] = 0; }
+      for (int s = 0; s < NSLOT; ++s) { remaining[s] = iters_of_slot(s) * GEO_NSTAGE; stage[s] = 0; par[s] = 0; }
       while (remaining[0] > 0 || remaining[1] > 0) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-          if (remaining[s] > 0 && tc::mbar_test_wait(&bars[1 + 3 * s], par[s])) {
+          if (remaining[s] > 0 && tc::mbar_test_wait(&bars[1 + 2 * s], par[s])) {
             tc::fence_after_sync();
-            issue_stage(tbase + (uint32_t)s * 256u, 128u, wsmem, 0u, plan, stage[s]);
-            if (two_term) tc::mbar_arrive(&bars[3 + 3 * s]);         // lo issuer may now accumulate on top
-            else tc::mbar_arrive(&bars[2 + 3 * s]);                  // no lo pass: stand in for its commit
-            tc::mma_commit(&bars[2 + 3 * s]);
+            issue_stage_pair(tbase + (uint32_t)s * 256u, wsmem, WBYTES / 2u, plan, stage[s], two_term != 0);
+            tc::mma_commit2(&bars[2 + 2 * s]);
             par[s] ^= 1u;
             stage[s] = stage[s] + 1 == GEO_NSTAGE ? 0 : stage[s] + 1;
             --remaining[s];
@@ -680,56 +649,33 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
         }
       }
     }
-  } else if (warp == 9 || warp == 10) {
-    // ---- lo issuers (one per slot): stream the W_lo tiles from L2 through a private TMA ring.  The chunks of the NEXT
-    // stage are requested as soon as the current one is committed (weights do not depend on the data), so their L2
-    // latency hides behind the rows' epilogue.
-    const int s = warp - 9;
-    const int my_tiles = tiles_of_slot(s);
-    if (lane == 0 && my_tiles > 0 && two_term) {
-      constexpr int NR = NRING / NSLOT;
-      LoRing rg;
-      rg.base_ptr = wsm + WBYTES + (size_t)s * NR * RING_SLOT;
-      rg.base = tc::smem_u32(rg.base_ptr);
-      rg.full = &bars[1 + 3 * NSLOT + s * NR];
-      rg.empty = &bars[1 + 3 * NSLOT + NRING + s * NR];
-      rg.full_par = 0; rg.empty_par = 0; rg.head = 0; rg.n = NR;
-      int remaining = my_tiles * TC_NLO, stage = 0;
-      uint32_t par_hi = 0;
-      int pf = ring_prefetch(rg, wlo, plan, 0);
-      while (remaining > 0) {
-        tc::mbar_wait(&bars[3 + 3 * s], par_hi);   // hi issuer has put the accumulator-initialising MMAs in the pipe
-        par_hi ^= 1u;
-        tc::fence_after_sync();
-        issue_stage_lo(tbase + (uint32_t)s * 256u, rg, wlo, plan, stage, pf);
-        tc::mma_commit(&bars[2 + 3 * s]);
-        stage = stage + 1 == TC_NLO ? 0 : stage + 1;
-        --remaining;
-        pf = remaining > 0 ? ring_prefetch(rg, wlo, plan, stage) : 0;
-      }
-    }
   } else {
     const int slot = warp / ROW_WARPS, roww = warp % ROW_WARPS;
     RowCtx cx;
     const uint32_t tm = tbase + (uint32_t)slot * 256u + ((uint32_t)(roww * 32) << 16);
     cx.R0 = tm; cx.R1 = tm + 128u;
-    cx.a_ready = &bars[1 + 3 * slot];
-    cx.acc_ready = &bars[2 + 3 * slot];
+    cx.a_ready = &bars[1 + 2 * slot];
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl) : "r"(tc::smem_u32(cx.a_ready)), "r"(0u));
+    cx.acc_ready = &bars[2 + 2 * slot];
     cx.ph = 0;
     cx.gb = 3 * (lane / 3);
     cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
     cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
-    cx.tim = (timing != nullptr && warp == 0 && lane == 0) ? timing : nullptr;
+    cx.tim = (timing != nullptr && blockIdx.x % 2 == 0 && warp == 0 && lane == 0) ? timing : nullptr;
     cx.st = 0; cx.st0 = 0; cx.st1 = GEO_NSTAGE;
-    for (int tile = blockIdx.x * NSLOT + slot; tile < ntiles; tile += gridDim.x * NSLOT) {
-      long long t0 = cx.tim ? clock64() : 0;
-      geo_tile<NK>(scs, C, src, list, count, tile, cx, roww, lane, query_mode, out5, lat_out, list2, count2);
-      if (cx.tim) { atomicAdd(&cx.tim[12], (unsigned long long)(clock64() - t0)); atomicAdd(&cx.tim[13], 1ull); }
+    if (ntiles > 0) {
+      for (int P = cl * NSLOT + slot; 2 * P < ntiles; P += ncl * NSLOT) {
+        long long t0 = cx.tim ? clock64() : 0;
+        // a tile index past the end is a ghost tile: it replays the last sample, takes part in every barrier, writes nothing
+        geo_tile<NK>(scs, C, src, list, count, 2 * P + (int)rank, cx, roww, lane, query_mode, out5, lat_out, list2, count2);
+        if (cx.tim) { atomicAdd(&cx.tim[12], (unsigned long long)(clock64() - t0)); atomicAdd(&cx.tim[13], 1ull); }
+      }
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tbase, 512);
+  tc::cluster_sync_all();     // the peer's TMEM / barriers must outlive the leader's last MMA and commit
+  if (warp == 8) tc::tmem_dealloc2(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -794,6 +740,7 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
     const uint32_t tm = tbase + (uint32_t)slot * 128u + ((uint32_t)(roww * 32) << 16);
     cx.R0 = tm; cx.R1 = tm + 64u;
     cx.a_ready = &bars[1 + 2 * slot];
+    cx.a_ready_cl = 0;
     cx.acc_ready = &bars[2 + 2 * slot];
     cx.ph = 0;
     cx.gb = 3 * (lane / 3);
@@ -819,11 +766,11 @@ size_t tc_weight_lo_bytes(int n_kpt) { return make_tc_plan(n_kpt).st[TC_NLO].off
 bool tc_supported(int n_views, int n_kpt, int sp_level) { return n_views == 3 && (n_kpt == 18 || n_kpt == 24) && sp_level == 3; }
 
 template <int NK>
-static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wlo, const SampleSrc& src,
-                                  const int* list, const int* counter, long long n_max, int query_mode, float* out5, uint4* lat,
-                                  int2* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
+static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term,
+                                  const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
+                                  uint4* lat, int2* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
   constexpr TcPlan plan = make_tc_plan(NK);
-  const size_t smem_geo = plan.st[GEO_NSTAGE].off + (size_t)(NK <= 18 ? 12 : 10) * RING_SLOT;
+  const size_t smem_geo = plan.st[GEO_NSTAGE].off;
   const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
   static bool attr = false;
   if (!attr) {
@@ -834,26 +781,29 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
     attr = true;
   }
   const long long max_tiles = (n_max + SPT - 1) / SPT;
-  long long g = (max_tiles + NSLOT - 1) / NSLOT;
-  int grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
-  shade_geo_kernel<NK><<<grid, TC_THREADS, smem_geo, st>>>(sc, C, wblob, wlo, src, list, counter, query_mode, out5, lat, list2, count2,
-                                                          timing);
+  long long pairs = (max_tiles + 2 * NSLOT - 1) / (2 * NSLOT);   // clusters that can have work
+  const int max_clusters = num_sms / 2;
+  int grid = 2 * (int)(pairs < 1 ? 1 : (pairs > max_clusters ? max_clusters : pairs));
+  shade_geo_kernel<NK><<<grid, TC_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, out5, lat, list2,
+                                                          count2, timing);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  g = (max_tiles + CSLOT - 1) / CSLOT;
+  long long g = (max_tiles + CSLOT - 1) / CSLOT;
   grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
   shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, count2, lat, out5, timing);
   return cudaGetLastError();
 }
 
-cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wlo, int n_kpt, const SampleSrc& src,
-                            const int* list, const int* counter, long long n_max, int query_mode, float* out5, void* lat_scratch,
-                            void* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
+cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term, int n_kpt,
+                            const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
+                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
   if (n_kpt == 18)
-    return launch_tc_impl<18>(sc, C, wblob, wlo, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch, (int2*)list2, count2,
-                              num_sms, st, timing);
-  return launch_tc_impl<24>(sc, C, wblob, wlo, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch, (int2*)list2, count2,
-                            num_sms, st, timing);
+    return launch_tc_impl<18>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
+                              (int2*)list2, count2, num_sms, st, timing);
+  return launch_tc_impl<24>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
+                            (int2*)list2, count2, num_sms, st, timing);
 }
+
+size_t tc_pair_blob_bytes(int n_kpt) { return 2 * (size_t)make_tc_plan(n_kpt).st[GEO_NSTAGE].off; }
 
 }  // namespace kpn

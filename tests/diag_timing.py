@@ -18,4 +18,5 @@ for eng in (2, 0):
     o = np.array(list(out), dtype=np.float64)
     tiles = max(o[13], 1)
     print(f"engine {eng}: tiles recorded {int(o[13])}, cycles/tile {o[12]/tiles:.0f}, total wait/tile {o[:12].sum()/tiles:.0f} ({100*o[:12].sum()/o[12]:.1f}%)")
+    print(f"   colour kernel: tiles {int(o[15])}, cycles/tile {o[14]/max(o[15],1):.0f}")
     print("   wait cycles per stage:", ", ".join(f"{n}={o[i]/tiles:.0f}" for i, n in enumerate(names)))

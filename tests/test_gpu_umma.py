@@ -26,3 +26,19 @@ def test_umma_tile(N, K, variant):
     ref = A.float() @ B.float().t()
     err = (D - ref).abs().max().item()
     assert err < 2e-3, f"variant {variant} N={N} K={K}: max err {err}"
+
+
+@pytest.mark.parametrize("N,K", [(128, 192), (128, 128), (128, 144), (64, 128), (96, 128), (64, 64), (128, 240), (32, 32)])
+def test_umma_cta_pair_tile(N, K):
+    """cta_group::2: one 256 x N x K tile on a 2-CTA cluster, each CTA holding half of B's rows."""
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + K + 7)
+    A = (torch.randn(256, K, generator=g) * 0.5).half().cuda()
+    B = (torch.randn(N, K, generator=g) * 0.5).half().cuda()
+    D = torch.full((256, N), float("nan"), device="cuda")
+    rc = lib.kpn_selftest_umma2(N, K, A.data_ptr(), B.data_ptr(), D.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    err = (D - ref).abs().max().item()
+    assert err < 2e-3, f"N={N} K={K}: max err {err}"
