@@ -178,7 +178,7 @@ int kpn_set_profiling(kpn_ctx* ctx, int enable);
  * on one CTA through tcgen05.mma.  Device pointers.  variant bit0: B core-matrix arrangement, bit1: A from shared memory. */
 int kpn_selftest_umma(int N, int K, const void* A, const void* B, float* D, int variant, void* stream);
 /* Same for the CTA-pair form (cta_group::2): D(256,N) = A(256,K) * B(N,K)^T on a 2-CTA cluster. */
-int kpn_selftest_umma2(int N, int K, const void* A, const void* B, float* D, void* stream);
+int kpn_selftest_umma2(int N, int K, const void* A, const void* B, float* D, int a_col, int d_col, int mode, void* stream);
 
 #ifdef __cplusplus
 }

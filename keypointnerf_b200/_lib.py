@@ -102,7 +102,7 @@ def load() -> C.CDLL:
     lib.kpn_set_profiling.restype = C.c_int
     lib.kpn_debug_timing.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.kpn_debug_timing.restype = C.c_int
-    lib.kpn_selftest_umma2.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.kpn_selftest_umma2.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.kpn_selftest_umma2.restype = C.c_int
     lib.kpn_selftest_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.kpn_selftest_umma.restype = C.c_int

@@ -209,23 +209,25 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
     std::vector<__half> pair(tc_pair_blob_bytes(w->n_kpt) / 2, __float2half_rn(0.0f));   // [rank][hi halves | lo halves]
     // stage -> (layer, first row in the tile); stage 4 stacks the density layer 0 and the colour compress layer
     const int stage_layer[TC_NSTAGE] = {L_GEO0, L_GEO1, L_GEO2, L_GEO3, L_DEN0, L_DEN1, L_BASE0, L_BASE1, L_VIS1A, L_VIS1B, L_VIS2A, L_OUT0};
+    auto put_one = [&](int stage, int n, int kk, float wv) {
+      const int Np = plan.st[stage].Np;
+      const size_t at = (plan.st[stage].off + tc::core_offset_bytes(n, kk, Np)) / 2;
+      const __half hi = __float2half_rn(wv);
+      blob[at] = hi;
+      if (stage < 6) {   // geometry stages: row n of the tile goes to CTA rank n / (Np/2), as row n % (Np/2) of its half tile
+        const int Nh = Np / 2, rk = n / Nh;
+        const size_t half_at = ((size_t)rk * geo_bytes + plan.st[stage].off / 2 + tc::core_offset_bytes(n % Nh, kk, Nh)) / 2;
+        pair[half_at] = hi;
+        pair[half_at + geo_bytes / 4] = __float2half_rn(wv - __half2float(hi));   // lo halves follow the hi halves
+      }
+    };
     auto put = [&](int stage, int layer, int row0) {
       const kpn_layer& L = w->layer[layer];
-      const int Np = plan.st[stage].Np;
-      for (int o = 0; o < L.n_out; ++o)
+      for (int o = 0; o < L.n_out; ++o) {
         for (int i = 0; i < L.n_in; ++i)
-        {
-          const size_t at = (plan.st[stage].off + tc::core_offset_bytes(row0 + o, i, Np)) / 2;
-          const float wv = We[layer][(size_t)o * L.n_in + i];
-          const __half hi = __float2half_rn(wv);
-          blob[at] = hi;
-          if (stage < 6) {   // geometry stages: row n of the tile goes to CTA rank n / (Np/2), as row n % (Np/2) of its half tile
-            const int n = row0 + o, Nh = Np / 2, rk = n / Nh;
-            const size_t half_at = ((size_t)rk * geo_bytes + plan.st[stage].off / 2 + tc::core_offset_bytes(n % Nh, i, Nh)) / 2;
-            pair[half_at] = hi;
-            pair[half_at + geo_bytes / 4] = __float2half_rn(wv - __half2float(hi));   // lo halves follow the hi halves
-          }
-        }
+          put_one(stage, row0 + o, stage < 6 ? tc_kmap(stage, w->n_kpt, i) : i, We[layer][(size_t)o * L.n_in + i]);
+        if (stage < 6) put_one(stage, row0 + o, tc_kbias(stage, w->n_kpt), L.bias[o]);   // bias row (activation column == 1)
+      }
     };
     for (int sidx = 0; sidx < TC_NSTAGE; ++sidx) put(sidx, stage_layer[sidx], 0);
     put(4, L_CMP, 64);
@@ -236,8 +238,6 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
     TcConsts& T = c->tcc;
     memset(&T, 0, sizeof(T));
     auto bias = [&](int layer, float* dst) { for (int o = 0; o < w->layer[layer].n_out; ++o) dst[o] = w->layer[layer].bias[o]; };
-    bias(L_GEO0, T.b_l0); bias(L_GEO1, T.b_l1); bias(L_GEO2, T.b_l2); bias(L_GEO3, T.b_l3);
-    bias(L_DEN0, T.b_p0); bias(L_CMP, T.b_cmp); bias(L_DEN1, T.b_p1);
     bias(L_BASE0, T.b_base0); bias(L_BASE1, T.b_base1); bias(L_VIS1A, T.b_vis1a); bias(L_VIS1B, T.b_vis1b);
     bias(L_VIS2A, T.b_vis2a); bias(L_OUT0, T.b_out0);
     for (int o = 0; o < 2; ++o) { for (int i = 0; i < 64; ++i) T.w_p2[o][i] = We[L_DEN2][o * 64 + i]; T.b_p2[o] = w->layer[L_DEN2].bias[o]; }

@@ -89,7 +89,8 @@ umma_selftest_kernel(int N, int K, const __half* __restrict__ A, const __half* _
 // 2-CTA variant: D[256][N] = A[256][K] * B[N][K]^T.  CTA r holds rows 128r..128r+127 of A (TMEM) and rows
 // r*N/2 .. (r+1)*N/2-1 of B (shared memory, [k/8][n/8] core-matrix order with N/2 rows).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-umma2_selftest_kernel(int N, int K, const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D) {
+umma2_selftest_kernel(int N, int K, const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D, int a_col,
+                      int d_col, int mode) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_a, bar_acc;
   __shared__ uint32_t tmem_base_s;
@@ -109,7 +110,6 @@ umma2_selftest_kernel(int N, int K, const __half* __restrict__ A, const __half* 
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
   const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
-  const uint32_t a_col = 0, d_col = 256;
   const __half* arow = A + (size_t)(rank * 128 + t) * K;
   for (int kc = 0; kc < K / 16; ++kc) {
     uint32_t r[8];
@@ -120,16 +120,34 @@ umma2_selftest_kernel(int N, int K, const __half* __restrict__ A, const __half* 
   tc::wait_st();
   tc::fence_before_sync();
   tc::mbar_arrive_cluster(&bar_a, 0);   // every row thread of both CTAs arrives on the LEADER's barrier
-  if (rank == 0 && t == 0) {
+  const uint32_t idesc = tc::make_idesc_f16(256, N);
+  const uint32_t lbo = (uint32_t)(Nh / 8) * 128u;
+  if (mode == 0) {          // one thread issues
+    if (rank == 0 && t == 0) {
+      tc::mbar_wait(&bar_a, 0);
+      tc::fence_after_sync();
+      for (int j = 0; j < K / 16; ++j) {
+        uint64_t bd = tc::make_smem_desc(tc::smem_u32(smem) + j * 2 * lbo, lbo, 128u);
+        tc::mma_ts2(tbase + d_col, tbase + a_col + j * 8, bd, idesc, j > 0);
+      }
+      tc::mma_commit2(&bar_acc);
+    }
+  } else if (rank == 0 && warp == 0) {   // warp-converged issue: every lane runs the code, the elected lane's MMAs take effect
+    const uint32_t el = tc::elect_one();
     tc::mbar_wait(&bar_a, 0);
     tc::fence_after_sync();
-    const uint32_t idesc = tc::make_idesc_f16(256, N);
-    const uint32_t lbo = (uint32_t)(Nh / 8) * 128u;
-    for (int j = 0; j < K / 16; ++j) {
-      uint64_t bd = tc::make_smem_desc(tc::smem_u32(smem) + j * 2 * lbo, lbo, 128u);
-      tc::mma_ts2(tbase + d_col, tbase + a_col + j * 8, bd, idesc, j > 0);
+    const uint32_t b0 = ((tc::smem_u32(smem) >> 4) & 0x3FFFu) + ((lbo >> 4) << 16);
+    const uint32_t dhi = (128u >> 4) | (1u << 14);
+    if (mode == 1) {
+      for (int j = 0; j < K / 16; ++j)
+        tc::mma_ts2_el(tbase + d_col, tbase + a_col + j * 8, b0 + (uint32_t)j * ((2u * lbo) >> 4), dhi, idesc, j > 0, el);
+      tc::mma_commit2_el(&bar_acc, el);
+    } else if (el) {                      // mode 2: the elected lane alone takes the branch
+      for (int j = 0; j < K / 16; ++j)
+        tc::mma_ts2_el(tbase + d_col, tbase + a_col + j * 8, b0 + (uint32_t)j * ((2u * lbo) >> 4), dhi, idesc, j > 0, 1u);
+      tc::mma_commit2_el(&bar_acc, 1u);
     }
-    tc::mma_commit2(&bar_acc);
+    __syncwarp();
   }
   tc::mbar_wait(&bar_acc, 0);
   tc::fence_after_sync();
@@ -148,13 +166,16 @@ umma2_selftest_kernel(int N, int K, const __half* __restrict__ A, const __half* 
 
 }  // namespace kpn
 
-// 2-CTA self-test: A (256,K) fp16, B (N,K) fp16, D (256,N) fp32: device pointers.  N % 32 == 0.
-extern "C" int kpn_selftest_umma2(int N, int K, const void* A, const void* B, float* D, void* stream) {
+// 2-CTA self-test: A (256,K) fp16, B (N,K) fp16, D (256,N) fp32: device pointers.  N % 32 == 0.  a_col / d_col: tensor-memory
+// columns of the activation tile and the accumulator; mode 0: one issuing thread, 1: warp-converged issue with an elected lane
+// (predicated MMAs), 2: elected lane takes a branch.
+extern "C" int kpn_selftest_umma2(int N, int K, const void* A, const void* B, float* D, int a_col, int d_col, int mode, void* stream) {
   if (N % 32 || N < 32 || N > 256 || K % 16 || K < 16 || K > 256) return -1;
+  if (a_col < 0 || a_col % 8 || d_col % 8 || a_col + K / 2 > d_col || d_col + N > 512 || mode < 0 || mode > 2) return -1;
   size_t smem = (size_t)(N / 2) * K * 2;
   cudaError_t e = cudaFuncSetAttribute(kpn::umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -2;
-  kpn::umma2_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(N, K, (const __half*)A, (const __half*)B, D);
+  kpn::umma2_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(N, K, (const __half*)A, (const __half*)B, D, a_col, d_col, mode);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

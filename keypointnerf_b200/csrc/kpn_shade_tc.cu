@@ -23,6 +23,7 @@
 //         4 P0|CMP 128->64|24 R1->R0 | 5 P1 64->64 R0->R1
 //   colour 6 BASE0 105->64 R0->R1 | 7 BASE1 64->32 R1->R0 | 8 VIS1A 32->32 R0->R1 | 9 VIS1B 32->33 R1->R0
 //         10 VIS2A 32->32 R0->R1 | 11 OUT0 37->16 R1->R0
+#include <cstdlib>
 #include "kpn_device.cuh"
 #include "kpn_launch.h"
 #include "kpn_tc.cuh"
@@ -33,7 +34,6 @@ namespace {
 
 constexpr int ROW_WARPS = 4;
 constexpr int NSLOT = 2;                                  // geo kernel tile slots
-constexpr int TC_THREADS = (NSLOT * ROW_WARPS + 1) * 32;  // 288: 8 row warps + allocator/issuer warp
 constexpr int CSLOT = 3;                                  // colour kernel tile slots
 constexpr int TCC_THREADS = (CSLOT * ROW_WARPS + 1) * 32; // 416: 12 row warps + issuer
 constexpr int GEO_NSTAGE = 6, COL_NSTAGE = 6;
@@ -167,18 +167,100 @@ __device__ __forceinline__ void encode_fast(const SceneS& S, int v, int k, const
   e[0] = dz * w; e[1] = s * w; e[2] = co * w; e[3] = s2 * w; e[4] = c2 * w; e[5] = s4 * w; e[6] = c4 * w;
 }
 
+// =====================================================================================================================
+// geometry + density pass: two threads per row (column halves h = 0/1 in different warps of the same TMEM lane quarter)
+// =====================================================================================================================
+// Tensor-memory columns of one slot (256): the activation tile A (packed fp16 pairs) always starts at column 0, the fp32
+// accumulator D of a stage sits at geo_dcol(stage); a stage's A is rebuilt while the previous stage's D is being read.
+//   stage  A columns                                                           D columns
+//   0 L0   [0,K0P/2): thread 0 run | thread 1 run (tc_kmap)                      [128,256)
+//   1 L1   [0,64) act | [64,72) bias chunk                                       [128,256)
+//   2 L2   [0,64) act | [64,68) feat8 | 68 bias | [69,72) 0                      [128,256)
+//   3 L3   [0,60) act | 60 bias | [61,64) 0                                      [192,256)
+//   4 P0|C [0,32) mean hi | [32,64) var hi | [64,96) mean lo | [96,128) var lo | [128,136) bias chunk    [160,256)
+//   5 P1   [0,32) act hi | [32,64) act lo | [64,72) bias chunk                   [128,192)
+__host__ __device__ constexpr int geo_dcol(int stage) { return stage == 3 ? 192 : stage == 4 ? 160 : 128; }
+
+constexpr uint32_t H2_ONE = 0x00003C00u;   // fp16 pair (1.0, 0.0): the activation column that multiplies the bias row
+
+struct GeoXch { float g0, rad; uint32_t lat[6]; };   // what the h = 1 thread of a row hands to its h = 0 partner (32 bytes)
+
+struct GeoCtx {
+  uint32_t tm;          // TMEM address of the slot with this warp's lane quarter
+  uint32_t a_ready_cl;  // cluster-mapped shared address of the LEADER CTA's a_ready barrier of this slot
+  uint64_t* acc_ready;  // this CTA's copy of the slot's accumulator barrier
+  uint32_t ph;
+  int l1, l2;           // the other two lanes of this row's 3-view group
+};
+
+__device__ __forceinline__ void geo_signal(const GeoCtx& c, int lane) {
+  tc::wait_st();
+  tc::fence_before_sync();
+  __syncwarp();
+  if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(c.a_ready_cl) : "memory");
+}
+__device__ __forceinline__ void geo_wait(GeoCtx& c) {
+  tc::mbar_wait(c.acc_ready, c.ph);
+  c.ph ^= 1u;
+  tc::fence_after_sync();
+}
+__device__ __forceinline__ float gsum(const GeoCtx& c, float x) {
+  return x + __shfl_sync(FULL, x, c.l1) + __shfl_sync(FULL, x, c.l2);
+}
+
+// softplus(beta=100) of two accumulators -> packed fp16 pair.  max(x,0) in fp32; the correction log1p(exp(-100|x|))/100 <= 0.00693
+// from ONE ex2 per element and a cubic in e = exp(-100|x|) evaluated on packed halves (max error of the polynomial 7e-7, of
+// the fp16 evaluation 7e-6: below the rounding of the fp16 result itself for every |x| > 0.004).
+__device__ __forceinline__ uint32_t sp_pair(uint32_t a0, uint32_t a1) {
+  const float x0 = u2f(a0), x1 = u2f(a1);
+  const float e0 = ex2f(-100.0f * LOG2E * fabsf(x0)), e1 = ex2f(-100.0f * LOG2E * fabsf(x1));
+  const __half2 e = __floats2half2_rn(e0, e1);
+  const uint32_t k3 = 0x90d090d0u, k2 = 0x189f189fu, k1 = 0x9cd39cd3u, k0 = 0x211b211bu;   // -5.875e-4, 2.2564e-3, -4.7112e-3, 9.9716e-3
+  __half2 pl = __hfma2(e, *reinterpret_cast<const __half2*>(&k3), *reinterpret_cast<const __half2*>(&k2));
+  pl = __hfma2(pl, e, *reinterpret_cast<const __half2*>(&k1));
+  pl = __hfma2(pl, e, *reinterpret_cast<const __half2*>(&k0));
+  pl = __hmul2(pl, e);
+  const __half2 y = __hadd2(__floats2half2_rn(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)), pl);
+  return *reinterpret_cast<const uint32_t*>(&y);
+}
+
+// store N registers to consecutive tensor-memory columns starting at column C0 (relative alignment known at compile time)
+template <int N, int C0>
+__device__ __forceinline__ void st_cols(uint32_t addr, const uint32_t* r) {
+  if constexpr (N >= 32 && C0 % 32 == 0) { tc::tmem_st32(addr, r); st_cols<N - 32, C0 + 32>(addr + 32, r + 32); }
+  else if constexpr (N >= 16 && C0 % 16 == 0) { tc::tmem_st16(addr, r); st_cols<N - 16, C0 + 16>(addr + 16, r + 16); }
+  else if constexpr (N >= 8 && C0 % 8 == 0) { tc::tmem_st8(addr, r); st_cols<N - 8, C0 + 8>(addr + 8, r + 8); }
+  else static_assert(N == 0, "run is not a multiple of 8 columns");
+}
+
+// epilogue of a 128-wide softplus stage: this thread's 64 accumulator columns at d -> 32 packed columns at a.
+// bias_tail: the last 4 packed columns become (1,0),0,0,0 (layer-3 input: bias column + K padding).
+__device__ __forceinline__ void geo_epi_sp(uint32_t d, uint32_t a, bool bias_tail) {
+  uint32_t r[64];
+  tc::tmem_ld32(d, r);
+  tc::tmem_ld32(d + 32, r + 32);
+  tc::wait_ld();
+  uint32_t o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = sp_pair(r[2 * i], r[2 * i + 1]);
+  tc::tmem_st16(a, o);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = sp_pair(r[32 + 2 * i], r[33 + 2 * i]);
+  if (bias_tail) { o[12] = H2_ONE; o[13] = 0u; o[14] = 0u; o[15] = 0u; }
+  tc::tmem_st16(a + 16, o);
+}
+
 template <int NK>
-__device__ __forceinline__ void geo_tile(const SceneS& sc, const TcConsts& C, const SampleSrc& src,
-                                         const int* __restrict__ list, int count, int tile, RowCtx& cx, int roww, int lane,
-                                         int query_mode, float* __restrict__ out5, uint4* __restrict__ lat_out,
-                                         int2* __restrict__ list2, int* __restrict__ count2) {
-  constexpr int ENC = 7 * NK;
-  constexpr int A0C = tc_k0p(NK) / 2;
-  const uint32_t R0 = cx.R0, R1 = cx.R1;
+__device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restrict__ wp2, GeoXch* __restrict__ xch,
+                                         const SampleSrc& src, const int* __restrict__ list, int count, int tile, GeoCtx& cx,
+                                         int q4, int h, int lane, int bar_id, int query_mode, float* __restrict__ out5,
+                                         uint4* __restrict__ lat_out, int2* __restrict__ list2, int* __restrict__ count2) {
+  constexpr int NP = NK / 2, PA = tc_l0_pa(NK), FA = tc_l0_fa(NK);
+  const uint32_t A = cx.tm;
   const int g = lane / 3;
   const int v = lane - 3 * g;           // lanes 30,31 replay views 0,1 of the warp's last sample (results unused)
-  const int si = tile * SPT + roww * SPW + min(g, SPW - 1);
-  const bool writer = (lane < 3 * SPW) && (v == 0) && (si < count);
+  const int si = tile * SPT + q4 * SPW + min(g, SPW - 1);
+  const bool writer = (h == 0) && (lane < 3 * SPW) && (v == 0) && (si < count);
   const int id = list[min(si, count - 1)];
   float p[3], d[3];
   fetch_sample(src, id, p, d);
@@ -186,9 +268,8 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const TcConsts& C, co
   const float bw = boundary_weight_fast(q);
   const float pw = bw / (gsum(cx, bw) + 1e-6f);  // reference src/model.py:750-759 (mask == 1 for shaded samples)
 
-  // ---- stage 0 input: [encoding 7*NK | feat64 64 | 0-pad] -> fp16 -> TMEM R0
+  // ---- stage 0 input (reference src/spatial.py:63-118 encoding | src/utils.py:74-89 feat64 gather), column order tc_kmap
   {
-    uint32_t a[A0C];
     float c[3];
     {
       const float* E = sc.E[v];
@@ -196,109 +277,162 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const TcConsts& C, co
       c[1] = E[4] * p[0] + E[5] * p[1] + E[6] * p[2] + E[7];
       c[2] = E[8] * p[0] + E[9] * p[1] + E[10] * p[2] + E[11];
     }
-#pragma unroll
-    for (int k = 0; k < NK; k += 2) {
-      float e0[7], e1[7];
-      encode_fast(sc, v, k, c, e0);
-      encode_fast(sc, v, k + 1, c, e1);
-#pragma unroll
-      for (int r = 0; r < 7; ++r) a[(r * NK + k) / 2] = tc::pack_h2(e0[r], e1[r]);
-    }
     const Taps t64 = make_taps(q.u, q.v, sc.f64.W, sc.f64.H);
+    if (h == 0) {
+      constexpr int N0 = 7 * PA + FA / 2;
+      uint32_t a[N0];
 #pragma unroll
-    for (int cq = 0; cq < 4; ++cq) {
-      float f[16];
-      gather_f32<4>(sc.f64, v, t64, cq * 4, f);
+      for (int gq = 0; gq < FA / 4; ++gq) {
+        float f[4];
+        gather_f32<1>(sc.f64, v, t64, gq, f);
+        a[7 * PA + 2 * gq] = tc::pack_h2(f[0], f[1]);
+        a[7 * PA + 2 * gq + 1] = tc::pack_h2(f[2], f[3]);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[ENC / 2 + cq * 8 + i] = tc::pack_h2(f[2 * i], f[2 * i + 1]);
+      for (int j = 0; j < PA; ++j) {
+        float e0[7], e1[7];
+        encode_fast(sc, v, 2 * j, c, e0);
+        encode_fast(sc, v, 2 * j + 1, c, e1);
+#pragma unroll
+        for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
+      }
+      st_cols<N0, 0>(A, a);
+    } else {
+      constexpr int C1 = 7 * PA + FA / 2;           // first column of this thread's run
+      constexpr int NE = 7 * (NP - PA), NF = (64 - FA) / 2;
+      constexpr int N1 = tc_k0p(NK) / 2 - C1;
+      uint32_t a[N1];
+#pragma unroll
+      for (int gq = 0; gq < (64 - FA) / 4; ++gq) {
+        float f[4];
+        gather_f32<1>(sc.f64, v, t64, FA / 4 + gq, f);
+        a[NE + 2 * gq] = tc::pack_h2(f[0], f[1]);
+        a[NE + 2 * gq + 1] = tc::pack_h2(f[2], f[3]);
+      }
+#pragma unroll
+      for (int j = PA; j < NP; ++j) {
+        float e0[7], e1[7];
+        encode_fast(sc, v, 2 * j, c, e0);
+        encode_fast(sc, v, 2 * j + 1, c, e1);
+#pragma unroll
+        for (int r = 0; r < 7; ++r) a[7 * (j - PA) + r] = tc::pack_h2(e0[r], e1[r]);
+      }
+      a[NE + NF] = H2_ONE;
+#pragma unroll
+      for (int i = NE + NF + 1; i < N1; ++i) a[i] = 0u;
+      st_cols<N1, C1>(A + C1, a);
     }
-#pragma unroll
-    for (int i = ENC / 2 + 32; i < A0C; ++i) a[i] = 0u;
-#pragma unroll
-    for (int c0 = 0; c0 + 32 <= A0C; c0 += 32) tc::tmem_st32(R0 + c0, a + c0);
-    if (A0C % 32 >= 16) tc::tmem_st16(R0 + (A0C / 32) * 32, a + (A0C / 32) * 32);
-    if (A0C % 16 >= 8) tc::tmem_st8(R0 + (A0C / 16) * 16, a + (A0C / 16) * 16);
   }
-  signal_a(cx);
-  // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720)
-  wait_acc(cx);
-  epi_inplace<4, 1>(R1, R1, C.b_l0);
-  signal_a(cx);
-  wait_acc(cx);
-  epi_inplace<4, 1>(R0, R0, C.b_l1);
-  {
+  geo_signal(cx, lane);
+  const uint32_t dh = A + 128u + 64u * (uint32_t)h, ah = A + 32u * (uint32_t)h;
+  // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720); the h = 0 thread also writes the bias / feat8 chunk
+  geo_wait(cx);
+  geo_epi_sp(dh, ah, false);
+  if (h == 0) {
+    const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tc::tmem_st8(A + 64, b);
+  }
+  geo_signal(cx, lane);
+  geo_wait(cx);
+  geo_epi_sp(dh, ah, false);
+  if (h == 0) {
     const Taps t8 = make_taps(q.u, q.v, sc.f8.W, sc.f8.H);
     float g8[8];
     gather_f32<2>(sc.f8, v, t8, 0, g8);
-    uint32_t o[8] = {tc::pack_h2(g8[0], g8[1]), tc::pack_h2(g8[2], g8[3]), tc::pack_h2(g8[4], g8[5]), tc::pack_h2(g8[6], g8[7]),
-                     0u, 0u, 0u, 0u};
-    tc::tmem_st8(R0 + 64, o);
+    const uint32_t b[8] = {tc::pack_h2(g8[0], g8[1]), tc::pack_h2(g8[2], g8[3]), tc::pack_h2(g8[4], g8[5]), tc::pack_h2(g8[6], g8[7]),
+                           H2_ONE, 0u, 0u, 0u};
+    tc::tmem_st8(A + 64, b);
   }
-  signal_a(cx);
-  wait_acc(cx);
-  epi_inplace<4, 1>(R1, R1, C.b_l2);
-  signal_a(cx);
-  // ---- view pooling: weighted mean || variance over the 3 lanes of the group (src/utils.py:722-748)
-  wait_acc(cx);
-#pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
-    uint32_t r[32];
-    tc::tmem_ld32(R0 + ch * 32, r);
-    tc::wait_ld();
-    uint32_t om[16], ov[16], lm[16], lv[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float x0 = u2f(r[2 * i]) + C.b_l3[ch * 32 + 2 * i], x1 = u2f(r[2 * i + 1]) + C.b_l3[ch * 32 + 2 * i + 1];
-      float m0 = gsum(cx, pw * x0), m1 = gsum(cx, pw * x1);
-      float d0 = x0 - m0, d1 = x1 - m1;
-      float v0 = gsum(cx, pw * d0 * d0), v1 = gsum(cx, pw * d1 * d1);
-      split_h2(m0, m1, om[i], lm[i]);   // the density tail's inputs are kept to two fp16 terms (hi | lo)
-      split_h2(v0, v1, ov[i], lv[i]);
-    }
-    tc::tmem_st16(R1 + ch * 16, om);
-    tc::tmem_st16(R1 + 32 + ch * 16, ov);
-    tc::tmem_st16(R1 + 64 + ch * 16, lm);
-    tc::tmem_st16(R1 + 96 + ch * 16, lv);
-  }
-  signal_a(cx);
-  // ---- P0 (softplus) | compress (linear, kept in registers)  (src/utils.py:577-587, src/model.py:819)
-  wait_acc(cx);
-  float lat[24];
+  geo_signal(cx, lane);
+  geo_wait(cx);
+  geo_epi_sp(dh, ah, h == 1);
+  geo_signal(cx, lane);
+  // ---- view pooling: weighted mean || variance over the 3 lanes of the group (src/utils.py:722-748); this thread owns 32
+  //      of the 64 feature columns; the density tail's inputs are kept to two fp16 terms (hi | lo)
+  geo_wait(cx);
   {
     uint32_t r[32];
-    tc::tmem_ld32(R0 + 64, r);
+    tc::tmem_ld32(A + 192u + 32u * (uint32_t)h, r);
     tc::wait_ld();
 #pragma unroll
-    for (int i = 0; i < 24; ++i) lat[i] = u2f(r[i]) + C.b_cmp[i];
-  }
-  {
-    uint32_t r[64];
-    tc::tmem_ld32(R0, r);
-    tc::tmem_ld32(R0 + 32, r + 32);
-    tc::wait_ld();
-    uint32_t hi[32], lo[32];
+    for (int cb = 0; cb < 2; ++cb) {
+      uint32_t mh[8], vh[8], ml[8], vl[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      split_h2(sp_fast(u2f(r[2 * i]) + C.b_p0[2 * i]), sp_fast(u2f(r[2 * i + 1]) + C.b_p0[2 * i + 1]), hi[i], lo[i]);
-    tc::tmem_st32(R0, hi);
-    tc::tmem_st32(R0 + 32, lo);
-  }
-  signal_a(cx);
-  // ---- P1 (softplus) then the 64->2 density head in fp32 on the CUDA cores
-  wait_acc(cx);
-  float g0 = C.b_p2[0], rad = C.b_p2[1];
-#pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
-    uint32_t r[32];
-    tc::tmem_ld32(R1 + ch * 32, r);
-    tc::wait_ld();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float h = sp_fast(u2f(r[i]) + C.b_p1[ch * 32 + i]);
-      g0 = fmaf(C.w_p2[0][ch * 32 + i], h, g0);
-      rad = fmaf(C.w_p2[1][ch * 32 + i], h, rad);
+      for (int i = 0; i < 8; ++i) {
+        const float x0 = u2f(r[16 * cb + 2 * i]), x1 = u2f(r[16 * cb + 2 * i + 1]);
+        const float m0 = gsum(cx, pw * x0), m1 = gsum(cx, pw * x1);
+        const float d0 = x0 - m0, d1 = x1 - m1;
+        const float v0 = gsum(cx, pw * d0 * d0), v1 = gsum(cx, pw * d1 * d1);
+        split_h2(m0, m1, mh[i], ml[i]);
+        split_h2(v0, v1, vh[i], vl[i]);
+      }
+      const uint32_t col = A + 16u * (uint32_t)h + 8u * (uint32_t)cb;
+      tc::tmem_st8(col, mh);
+      tc::tmem_st8(col + 32, vh);
+      tc::tmem_st8(col + 64, ml);
+      tc::tmem_st8(col + 96, vl);
+    }
+    if (h == 0) {
+      const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tc::tmem_st8(A + 128, b);
     }
   }
+  geo_signal(cx, lane);
+  // ---- P0 (softplus, two fp16 terms out) | compress (linear; this thread keeps 12 of the 24 latent values as 6 fp16 pairs)
+  geo_wait(cx);
+  uint32_t latp[6];
+  {
+    uint32_t rc[16], r[32];
+    tc::tmem_ld8(A + 160u + 64u + 8u * (uint32_t)h, rc);        // h = 0: latent 0..15, h = 1: latent 8..23 (two naturally
+    tc::tmem_ld8(A + 160u + 72u + 8u * (uint32_t)h, rc + 8);    // aligned 8-column loads)
+    tc::tmem_ld32(A + 160u + 32u * (uint32_t)h, r);
+    tc::wait_ld();
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float l0 = u2f(h ? rc[4 + 2 * i] : rc[2 * i]), l1 = u2f(h ? rc[5 + 2 * i] : rc[2 * i + 1]);
+      latp[i] = tc::pack_h2(l0, l1);
+    }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) split_h2(sp_fast(u2f(r[2 * i])), sp_fast(u2f(r[2 * i + 1])), hi[i], lo[i]);
+    tc::tmem_st16(A + 16u * (uint32_t)h, hi);
+    tc::tmem_st16(A + 32u + 16u * (uint32_t)h, lo);
+    if (h == 0) {
+      const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tc::tmem_st8(A + 64, b);
+    }
+  }
+  geo_signal(cx, lane);
+  // ---- P1 (softplus) then the 64->2 density head in fp32 on the CUDA cores: each thread a partial dot over its 32 columns
+  geo_wait(cx);
+  float g0 = 0.0f, rad = 0.0f;
+  {
+    uint32_t r[32];
+    tc::tmem_ld32(A + 128u + 32u * (uint32_t)h, r);
+    tc::wait_ld();
+    const float4* w0 = reinterpret_cast<const float4*>(wp2 + 32 * h);
+    const float4* w1 = reinterpret_cast<const float4*>(wp2 + 64 + 32 * h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 a0 = w0[i], a1 = w1[i];
+      const float h0 = sp_fast(u2f(r[4 * i])), h1 = sp_fast(u2f(r[4 * i + 1])), h2 = sp_fast(u2f(r[4 * i + 2])), h3 = sp_fast(u2f(r[4 * i + 3]));
+      g0 = fmaf(a0.x, h0, g0); g0 = fmaf(a0.y, h1, g0); g0 = fmaf(a0.z, h2, g0); g0 = fmaf(a0.w, h3, g0);
+      rad = fmaf(a1.x, h0, rad); rad = fmaf(a1.y, h1, rad); rad = fmaf(a1.z, h2, rad); rad = fmaf(a1.w, h3, rad);
+    }
+  }
+  // ---- the h = 1 thread hands its partial sums and latent half to its partner (same row, other warp) through shared memory
+  GeoXch* xr = xch + (32 * q4 + lane);
+  if (h == 1) {
+    *reinterpret_cast<uint4*>(xr) = make_uint4(__float_as_uint(g0), __float_as_uint(rad), latp[0], latp[1]);
+    *(reinterpret_cast<uint4*>(xr) + 1) = make_uint4(latp[2], latp[3], latp[4], latp[5]);
+    __threadfence_block();
+    tc::named_arrive(bar_id, 64);
+    return;
+  }
+  tc::named_sync(bar_id, 64);
+  const uint4 x0 = *reinterpret_cast<const uint4*>(xr), x1 = *(reinterpret_cast<const uint4*>(xr) + 1);
+  g0 += __uint_as_float(x0.x) + wp2[128];
+  rad += __uint_as_float(x0.y) + wp2[129];
   // ---- outputs of the geometry pass: alpha / sdf (eval_func, src/model.py:978-997), the compressed latent for the colour
   //      pass, and the colour work list (a sample with alpha == 0 composites with weight exactly 0: skipping it is exact)
   {
@@ -318,11 +452,9 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const TcConsts& C, co
       if (need) {
         pos += __popc(m & ((1u << lane) - 1u));
         list2[pos] = make_int2(pos, id);
-        uint4 w[3];
-        uint32_t* wp = reinterpret_cast<uint32_t*>(w);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) wp[i] = tc::pack_h2(lat[2 * i], lat[2 * i + 1]);
-        lat_out[3ll * pos + 0] = w[0]; lat_out[3ll * pos + 1] = w[1]; lat_out[3ll * pos + 2] = w[2];
+        lat_out[3ll * pos + 0] = make_uint4(latp[0], latp[1], latp[2], latp[3]);
+        lat_out[3ll * pos + 1] = make_uint4(latp[4], latp[5], x0.z, x0.w);
+        lat_out[3ll * pos + 2] = x1;
       }
     }
   }
@@ -521,24 +653,37 @@ constexpr int TC_NLO = 6;          // stages with a W_lo pass
 // which region holds the stage's A operand (bit = 1: R1); D goes to the other one.  Stages 1,3,4,7,9,11.
 constexpr uint32_t A_IN_R1 = 0xA9Au;
 
-// CTA-pair MMAs of one geometry stage.  `wsmem`: shared address of this CTA's half-blob = [W_hi halves of stages 0..5 |
-// W_lo halves of stages 0..5]; a stage's half tile sits at plan offset / 2.
-__device__ __forceinline__ void issue_stage_pair(uint32_t slot_tm, uint32_t wsmem, uint32_t lo_base, const TcPlan& plan, int stage,
-                                                 bool two_term) {
-  const uint32_t a_r1 = (A_IN_R1 >> stage) & 1u;
-  const uint32_t a_tm = slot_tm + (a_r1 ? 128u : 0u), d_tm = slot_tm + (a_r1 ? 0u : 128u);
-  const int Kp = plan.st[stage].Kp, Np = plan.st[stage].Np;
-  const uint32_t lbo = (uint32_t)(Np / 16) * 128u;       // half tile: Np/2 rows -> (Np/2)/8 core matrices per K chunk
-  const uint32_t idesc = tc::make_idesc_f16(256, Np);
-  const uint32_t b_hi = wsmem + plan.st[stage].off / 2u, b_lo = b_hi + lo_base;
-  for (int j = 0; j < Kp / 16; ++j)
-    tc::mma_ts2(d_tm, a_tm + (uint32_t)j * 8u, tc::make_smem_desc(b_hi + (uint32_t)j * 2u * lbo, lbo, 128u), idesc, j > 0 ? 1u : 0u);
-  if (stage == 4 || stage == 5)   // density tail: activations come as hi | lo, the lo half sits Kp/2 columns further
-    for (int j = 0; j < Kp / 16; ++j)
-      tc::mma_ts2(d_tm, a_tm + (uint32_t)(Kp / 2) + (uint32_t)j * 8u, tc::make_smem_desc(b_hi + (uint32_t)j * 2u * lbo, lbo, 128u), idesc, 1u);
-  if (two_term)
-    for (int j = 0; j < Kp / 16; ++j)
-      tc::mma_ts2(d_tm, a_tm + (uint32_t)j * 8u, tc::make_smem_desc(b_lo + (uint32_t)j * 2u * lbo, lbo, 128u), idesc, 1u);
+// CTA-pair MMAs of one geometry stage, issued warp-converged (operands in uniform registers, one elected lane takes effect).
+// `wlo0`: low word of the shared-memory descriptor of this CTA's weight half-blob = [W_hi halves of stages 0..5 | W_lo halves]
+// (a stage's half tile sits at plan offset / 2; `lo_delta` = descriptor distance of the W_lo halves).  Per K chunk of 16 the
+// descriptor's start address advances by two core-matrix columns (2 * LBO).  Order: A_hi x W_hi, [A_hi x W_lo], [A_lo x W_hi].
+template <int NK, int STAGE>
+__device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint32_t lo_delta, bool two_term, uint32_t el) {
+  constexpr TcPlan plan = make_tc_plan(NK);
+  constexpr int Kp = plan.st[STAGE].Kp, Np = plan.st[STAGE].Np;
+  constexpr uint32_t lbo = (uint32_t)(Np / 16) * 128u;   // half tile: Np/2 rows -> (Np/2)/8 core matrices per K column of 8
+  constexpr uint32_t idesc = tc::make_idesc_f16(256, Np);
+  constexpr uint32_t dhi = (128u >> 4) | (1u << 14);     // SBO = 128 bytes, descriptor version 1
+  constexpr uint32_t step = (2u * lbo) >> 4;
+  constexpr int NCH = Kp / 16;                                        // weight K chunks incl. the bias chunk
+  constexpr int NACT = STAGE == 4 ? 8 : STAGE == 5 ? 4 : NCH;         // chunks whose activations are contiguous from column 0
+  constexpr int BIASCOL = STAGE == 4 ? 128 : 64;                      // column of the separate bias chunk (stages 4, 5)
+  constexpr int LOCOL = STAGE == 4 ? 64 : 32;                         // first column of the A_lo half (stages 4, 5)
+  const uint32_t b0 = wlo0 + ((plan.st[STAGE].off / 2u) >> 4) + ((lbo >> 4) << 16);
+  const uint32_t d_tm = slot_tm + (uint32_t)geo_dcol(STAGE);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+    tc::mma_ts2_el(d_tm, slot_tm + (uint32_t)(j < NACT ? 8 * j : BIASCOL), b0 + (uint32_t)j * step, dhi, idesc, j > 0 ? 1u : 0u, el);
+  if (two_term) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+      tc::mma_ts2_el(d_tm, slot_tm + (uint32_t)(j < NACT ? 8 * j : BIASCOL), b0 + lo_delta + (uint32_t)j * step, dhi, idesc, 1u, el);
+  }
+  if (STAGE >= 4) {
+#pragma unroll
+    for (int j = 0; j < NACT; ++j)
+      tc::mma_ts2_el(d_tm, slot_tm + (uint32_t)(LOCOL + 8 * j), b0 + (uint32_t)j * step, dhi, idesc, 1u, el);
+  }
 }
 
 // MMAs of one stage on resident weights.  `region` = width of the slot's R0/R1 regions, `wbase` = shared address the
@@ -586,20 +731,25 @@ __device__ __forceinline__ void load_weights(uint8_t* dst, const uint8_t* src, u
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// geometry + density kernel (CTA pairs)
+// geometry + density kernel (CTA pairs; 16 row warps = 2 slots x 4 TMEM lane quarters x 2 column halves, + 1 control warp)
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int GEO_ROW_WARPS = 16;
+constexpr int GEO_THREADS = (GEO_ROW_WARPS + 1) * 32;   // 544
+
 template <int NK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEO_THREADS, 1)
 shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
                  int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
                  int query_mode, float* __restrict__ out5, uint4* __restrict__ lat_out, int2* __restrict__ list2,
-                 int* __restrict__ count2, unsigned long long* __restrict__ timing) {
+                 int* __restrict__ count2, int issue_branch) {
   extern __shared__ __align__(1024) uint8_t wsm[];
-  // barriers: [0] weights | per slot s: [1+2s] a_ready (256 row threads of the pair; only the leader's copy is used),
-  //           [2+2s] acc_ready (one multicast commit per stage, each CTA waits on its own copy)
+  // barriers: [0] weights | per slot s: [1+2s] a_ready (one arrival per row warp of the pair = 16; only the leader's copy is
+  //           used), [2+2s] acc_ready (one multicast commit per stage, each CTA waits on its own copy)
   __shared__ uint64_t bars[1 + 2 * NSLOT];
   __shared__ uint32_t tmem_base_s;
   __shared__ SceneS scs;
+  __shared__ __align__(16) float wp2[132];                 // density head: w[0][64] | w[1][64] | b[2]
+  __shared__ __align__(16) GeoXch xch[NSLOT][128];
   constexpr TcPlan plan = make_tc_plan(NK);
   constexpr uint32_t WBYTES = plan.st[GEO_NSTAGE].off;   // per CTA: half of W_hi + half of W_lo of stages 0..5
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -607,16 +757,17 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
   const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int count = *count_ptr;
   const int ntiles = (count + SPT - 1) / SPT;
-  stage_scene(scs, *scp, NK, t, TC_THREADS);
+  stage_scene(scs, *scp, NK, t, GEO_THREADS);
+  for (int i = t; i < 130; i += GEO_THREADS) wp2[i] = i < 64 ? C.w_p2[0][i] : i < 128 ? C.w_p2[1][i - 64] : C.b_p2[i - 128];
 
-  if (warp == 8) tc::tmem_alloc2(&tmem_base_s, 512);
+  if (warp == GEO_ROW_WARPS) tc::tmem_alloc2(&tmem_base_s, 512);
   if (t == 0) {
     tc::mbar_init(&bars[0], 1);
-    for (int s = 0; s < NSLOT; ++s) { tc::mbar_init(&bars[1 + 2 * s], 2 * ROW_WARPS * 32); tc::mbar_init(&bars[2 + 2 * s], 1); }
+    for (int s = 0; s < NSLOT; ++s) { tc::mbar_init(&bars[1 + 2 * s], GEO_ROW_WARPS); tc::mbar_init(&bars[2 + 2 * s], 1); }
     tc::fence_mbar_init();
   }
   __syncthreads();
-  if (warp == 8 && lane == 0) load_weights(wsm, wpair + (size_t)rank * WBYTES, WBYTES, &bars[0]);   // this CTA's half-blob
+  if (warp == GEO_ROW_WARPS && lane == 0) load_weights(wsm, wpair + (size_t)rank * WBYTES, WBYTES, &bars[0]);   // this CTA's half-blob
   tc::fence_before_sync();
   __syncthreads();
   tc::cluster_sync_all();     // both CTAs: barriers initialised, TMEM allocated, weights resident
@@ -629,19 +780,37 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
     return n;
   };
 
-  if (warp == 8) {
-    if (lane == 0 && rank == 0 && ntiles > 0) {   // the pair's single MMA issuer
-      const uint32_t wsmem = tc::smem_u32(wsm);
+  if (warp == GEO_ROW_WARPS) {
+    if (rank == 0 && ntiles > 0) {   // the pair's MMA issuer: the whole warp runs the loop, one elected lane issues
+      const uint32_t el = tc::elect_one();
+      const uint32_t wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu;
       int remaining[NSLOT], stage[NSLOT];
       uint32_t par[NSLOT];
       for (int s = 0; s < NSLOT; ++s) { remaining[s] = iters_of_slot(s) * GEO_NSTAGE; stage[s] = 0; par[s] = 0; }
       while (remaining[0] > 0 || remaining[1] > 0) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-          if (remaining[s] > 0 && tc::mbar_test_wait(&bars[1 + 2 * s], par[s])) {
+          if (remaining[s] > 0 && __all_sync(FULL, tc::mbar_test_wait(&bars[1 + 2 * s], par[s]))) {
             tc::fence_after_sync();
-            issue_stage_pair(tbase + (uint32_t)s * 256u, wsmem, WBYTES / 2u, plan, stage[s], two_term != 0);
-            tc::mma_commit2(&bars[2 + 2 * s]);
+            const uint32_t stm = tbase + (uint32_t)s * 256u;
+            const uint32_t lod = (WBYTES / 2u) >> 4;
+            auto issue = [&](uint32_t e) {
+              switch (stage[s]) {
+                case 0: geo_issue<NK, 0>(stm, wlo0, lod, two_term != 0, e); break;
+                case 1: geo_issue<NK, 1>(stm, wlo0, lod, two_term != 0, e); break;
+                case 2: geo_issue<NK, 2>(stm, wlo0, lod, two_term != 0, e); break;
+                case 3: geo_issue<NK, 3>(stm, wlo0, lod, two_term != 0, e); break;
+                case 4: geo_issue<NK, 4>(stm, wlo0, lod, two_term != 0, e); break;
+                default: geo_issue<NK, 5>(stm, wlo0, lod, two_term != 0, e); break;
+              }
+              tc::mma_commit2_el(&bars[2 + 2 * s], e);
+            };
+            if (issue_branch) {          // debug knob (KPN_ISSUE_BRANCH=1): only the elected lane enters the issue code
+              if (el) issue(1u);
+              __syncwarp();
+            } else {
+              issue(el);
+            }
             par[s] ^= 1u;
             stage[s] = stage[s] + 1 == GEO_NSTAGE ? 0 : stage[s] + 1;
             --remaining[s];
@@ -650,32 +819,26 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
       }
     }
   } else {
-    const int slot = warp / ROW_WARPS, roww = warp % ROW_WARPS;
-    RowCtx cx;
-    const uint32_t tm = tbase + (uint32_t)slot * 256u + ((uint32_t)(roww * 32) << 16);
-    cx.R0 = tm; cx.R1 = tm + 128u;
-    cx.a_ready = &bars[1 + 2 * slot];
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl) : "r"(tc::smem_u32(cx.a_ready)), "r"(0u));
+    const int slot = warp >> 3, q4 = warp & 3, h = (warp >> 2) & 1;   // TMEM lane quarter = warp id % 4
+    GeoCtx cx;
+    cx.tm = tbase + (uint32_t)slot * 256u + ((uint32_t)(q4 * 32) << 16);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl) : "r"(tc::smem_u32(&bars[1 + 2 * slot])), "r"(0u));
     cx.acc_ready = &bars[2 + 2 * slot];
     cx.ph = 0;
-    cx.gb = 3 * (lane / 3);
-    cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
-    cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
-    cx.tim = (timing != nullptr && blockIdx.x % 2 == 0 && warp == 0 && lane == 0) ? timing : nullptr;
-    cx.st = 0; cx.st0 = 0; cx.st1 = GEO_NSTAGE;
-    if (ntiles > 0) {
-      for (int P = cl * NSLOT + slot; 2 * P < ntiles; P += ncl * NSLOT) {
-        long long t0 = cx.tim ? clock64() : 0;
-        // a tile index past the end is a ghost tile: it replays the last sample, takes part in every barrier, writes nothing
-        geo_tile<NK>(scs, C, src, list, count, 2 * P + (int)rank, cx, roww, lane, query_mode, out5, lat_out, list2, count2);
-        if (cx.tim) { atomicAdd(&cx.tim[12], (unsigned long long)(clock64() - t0)); atomicAdd(&cx.tim[13], 1ull); }
-      }
+    const int gb = 3 * (lane / 3);
+    cx.l1 = (gb + (lane - gb + 1) % 3) & 31;
+    cx.l2 = (gb + (lane - gb + 2) % 3) & 31;
+    const int bar_id = 1 + slot * 4 + q4;
+    for (int P = cl * NSLOT + slot; 2 * P < ntiles; P += ncl * NSLOT) {
+      // a tile index past the end is a ghost tile: it replays the last sample, takes part in every barrier, writes nothing
+      geo_tile<NK>(scs, wp2, xch[slot], src, list, count, 2 * P + (int)rank, cx, q4, h, lane, bar_id, query_mode, out5, lat_out,
+                   list2, count2);
     }
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::cluster_sync_all();     // the peer's TMEM / barriers must outlive the leader's last MMA and commit
-  if (warp == 8) tc::tmem_dealloc2(tbase, 512);
+  if (warp == GEO_ROW_WARPS) tc::tmem_dealloc2(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -784,8 +947,9 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   long long pairs = (max_tiles + 2 * NSLOT - 1) / (2 * NSLOT);   // clusters that can have work
   const int max_clusters = num_sms / 2;
   int grid = 2 * (int)(pairs < 1 ? 1 : (pairs > max_clusters ? max_clusters : pairs));
-  shade_geo_kernel<NK><<<grid, TC_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, out5, lat, list2,
-                                                          count2, timing);
+  static const int issue_branch = [] { const char* e = getenv("KPN_ISSUE_BRANCH"); return e && e[0] == '1' ? 1 : 0; }();
+  shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, out5, lat, list2,
+                                                           count2, issue_branch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   long long g = (max_tiles + CSLOT - 1) / CSLOT;

@@ -203,6 +203,34 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// ---- warp-converged issue: every lane runs the issue code (operands stay in uniform registers), one elected lane's
+//      instruction takes effect.  `el` = 1 in the elected lane (elect.sync picks the same lane for a given member mask).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p;
+}
+// CTA-pair MMA with the shared-memory descriptor given as two 32-bit halves (the high half is a per-kernel constant, the
+// low half advances by a compile-time step per K chunk) and an issue predicate.
+__device__ __forceinline__ void mma_ts2_el(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                           uint32_t accumulate, uint32_t el) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(el)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit2_el(uint64_t* bar, uint32_t el) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3), "r"(el)
+      : "memory");
+}
+// named barriers (ids 1..15): producer arrives, consumer syncs; `count` = threads of both sides
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // pack two floats to one register of fp16 pair: low half = a (even K index), high half = b
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);

@@ -9,7 +9,10 @@ namespace kpn {
 constexpr int TC_NSTAGE = 12;
 // stage:            0 L0   1 L1  2 L2  3 L3  4 P0|CMP 5 P1 6 BASE0 7 BASE1 8 VIS1A 9 VIS1B 10 VIS2A 11 OUT0
 // Np (padded N):    128    128   128   64    96       64   64      32      32      48      32       16
-// Kp (padded K):    K0P    128   144   128   128      64   112     64      32      32      32       48
+// Kp (padded K):    K0P    144   144   128   144      80   112     64      32      32      32       48
+// The geometry stages (0..5) carry their bias as one extra K row (the activation tile holds a constant 1 there), so their
+// epilogues have no per-column constants.  Stage 0 additionally permutes its inputs (tc_kmap) so that the two threads
+// that build a row's input each write one contiguous, naturally aligned run of tensor-memory columns.
 
 struct TcStage {
   int Kp, Np;
@@ -22,11 +25,41 @@ struct TcPlan {
   int K0P;  // padded input width of layer 0
 };
 
-__host__ __device__ constexpr int tc_k0p(int n_kpt) { return ((7 * n_kpt + 64) + 15) / 16 * 16; }
+// layer-0 input width incl. the bias row, padded to a multiple of 16
+__host__ __device__ constexpr int tc_k0p(int n_kpt) { return ((7 * n_kpt + 64 + 1) + 15) / 16 * 16; }
+// split of the layer-0 input between the two threads of a row: thread 0 builds keypoint pairs [0, PA) and feature
+// channels [0, FA), thread 1 the remaining pairs, the remaining channels and the bias column
+__host__ __device__ constexpr int tc_l0_pa(int n_kpt) { return n_kpt == 18 ? 6 : 8; }
+__host__ __device__ constexpr int tc_l0_fa(int n_kpt) { return n_kpt == 18 ? 12 : 16; }
+
+// K index (fp16 element of the activation row) that input `i` of geometry stage `stage` is multiplied with.
+// Stage 0 inputs: i < 7*n_kpt is encoding element r*n_kpt + k (reference src/spatial.py layout), else feat64 channel.
+__host__ __device__ constexpr int tc_kmap(int stage, int n_kpt, int i) {
+  if (stage != 0) return i;
+  const int NP = n_kpt / 2, PA = tc_l0_pa(n_kpt), FA = tc_l0_fa(n_kpt);
+  if (i < 7 * n_kpt) {
+    const int r = i / n_kpt, k = i % n_kpt, j = k / 2;
+    const int col = j < PA ? 7 * j + r : 7 * PA + FA / 2 + 7 * (j - PA) + r;
+    return 2 * col + (k & 1);
+  }
+  const int c = i - 7 * n_kpt;
+  return c < FA ? 2 * 7 * PA + c : 2 * (7 * PA + FA / 2 + 7 * (NP - PA)) + (c - FA);
+}
+// K index of the bias row of a geometry stage
+__host__ __device__ constexpr int tc_kbias(int stage, int n_kpt) {
+  switch (stage) {
+    case 0: return 2 * (7 * (n_kpt / 2) + 32);
+    case 1: return 128;
+    case 2: return 136;
+    case 3: return 120;
+    case 4: return 128;
+    default: return 64;
+  }
+}
 
 __host__ __device__ constexpr TcPlan make_tc_plan(int n_kpt) {
   TcPlan p{};
-  const int Kp[TC_NSTAGE] = {tc_k0p(n_kpt), 128, 144, 128, 128, 64, 112, 64, 32, 32, 32, 48};
+  const int Kp[TC_NSTAGE] = {tc_k0p(n_kpt), 144, 144, 128, 144, 80, 112, 64, 32, 32, 32, 48};
   const int Np[TC_NSTAGE] = {128, 128, 128, 64, 96, 64, 64, 32, 32, 48, 32, 16};
   uint32_t off = 0;
   for (int i = 0; i < TC_NSTAGE; ++i) {
@@ -43,9 +76,7 @@ __host__ __device__ constexpr TcPlan make_tc_plan(int n_kpt) {
 // fp32 constants, passed by value as a __grid_constant__ kernel parameter so that unrolled epilogues read
 // them as constant-bank operands.
 struct TcConsts {
-  float b_l0[128], b_l1[128], b_l2[128], b_l3[64];
-  float b_p0[64], b_cmp[32], b_p1[64];
-  float w_p2[2][64], b_p2[2];          // density head last layer (fp32 on CUDA cores)
+  float w_p2[2][64], b_p2[2];          // density head last layer (fp32 on CUDA cores); the geometry-stage biases ride in the MMAs
   float w_re0[16][4], b_re0[16];       // ray-direction encoder
   float w_re1[35][16], b_re1[35];
   float b_base0[64], b_base1[32], b_vis1a[32], b_vis1b[48], b_vis2a[32];
