@@ -191,13 +191,19 @@ struct GeoCtx {
   uint64_t* acc_ready;  // this CTA's copy of the slot's accumulator barrier
   uint32_t ph;
   int l1, l2;           // the other two lanes of this row's 3-view group
+  int relaxed;          // arrive without release semantics (default; KPN_RELAXED_ARRIVE=0 reverts): the activation tile lives in
+                        // tensor memory and is ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync; a release
+                        // would additionally drain the row's in-flight prefetch loads (measured: 40.4 -> 35.4 ms/frame)
 };
 
 __device__ __forceinline__ void geo_signal(const GeoCtx& c, int lane) {
   tc::wait_st();
   tc::fence_before_sync();
   __syncwarp();
-  if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(c.a_ready_cl) : "memory");
+  if (lane == 0) {
+    if (c.relaxed) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(c.a_ready_cl) : "memory");
+    else asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(c.a_ready_cl) : "memory");
+  }
 }
 __device__ __forceinline__ void geo_wait(GeoCtx& c) {
   tc::mbar_wait(c.acc_ready, c.ph);
@@ -250,9 +256,84 @@ __device__ __forceinline__ void geo_epi_sp(uint32_t d, uint32_t a, bool bias_tai
   tc::tmem_st16(a + 16, o);
 }
 
+// Gather staging (PREF): while a tile's layer-0 MMAs run, each row thread gathers the source-view features of its row of the
+// slot's NEXT tile (the long-latency part of the stage-0 input) into shared memory as packed fp16 pairs; the next tile's build
+// only copies them into tensor memory.  Words per row: 32 feat64 (thread 0 owns [0, FA/2), thread 1 the rest) + 2 x 4 feat8
+// (double-buffered by tile parity: it is consumed two stages after the next prefetch started).  Word w of row r sits at
+// [w * 128 + r] so that a warp's accesses are conflict free.
+constexpr int GEO_FW = 40;
+// shared memory holds the staging buffer next to the weights only for 18 keypoints (24: the layer-0 tile is 12 KB larger)
+__host__ __device__ constexpr bool geo_pref(int n_kpt) { return n_kpt == 18; }
+struct GeoPre { int id; float p[3]; };   // the sample this row shades in the slot's next tile
+
+// Asynchronous halves of a bilinear gather: issue the 4 tap loads of float4 groups [g0, g0 + NG) of a channel-last map now,
+// blend + pack + stage them after the next accumulator wait (the loads fly while the tensor core works).
+template <int NG>
+__device__ __forceinline__ void taps_issue(const MapDesc& m, int v, const Taps& t, int g0, float4 (&r)[2][4]) {
+  const int c4 = m.C >> 2;
+  const float4* base = (const float4*)m.ptr + (size_t)v * m.H * m.W * c4 + g0;
+  const float4* p00 = base + (size_t)t.o00 * c4;
+  const float4* p01 = base + (size_t)t.o01 * c4;
+  const float4* p10 = base + (size_t)t.o10 * c4;
+  const float4* p11 = base + (size_t)t.o11 * c4;
+#pragma unroll
+  for (int i = 0; i < NG; ++i) { r[i][0] = __ldg(p00 + i); r[i][1] = __ldg(p01 + i); r[i][2] = __ldg(p10 + i); r[i][3] = __ldg(p11 + i); }
+}
+template <int NG>
+__device__ __forceinline__ void taps_stage(const float (&w)[4], const float4 (&r)[2][4], uint32_t* __restrict__ fb, int word0) {
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    const float4 a = r[i][0], b = r[i][1], c = r[i][2], d = r[i][3];
+    const float f0 = a.x * w[0] + b.x * w[1] + c.x * w[2] + d.x * w[3], f1 = a.y * w[0] + b.y * w[1] + c.y * w[2] + d.y * w[3];
+    const float f2 = a.z * w[0] + b.z * w[1] + c.z * w[2] + d.z * w[3], f3 = a.w * w[0] + b.w * w[1] + c.w * w[2] + d.w * w[3];
+    fb[(word0 + 2 * i) * 128] = tc::pack_h2(f0, f1);
+    fb[(word0 + 2 * i + 1) * 128] = tc::pack_h2(f2, f3);
+  }
+}
+
 template <int NK>
+__device__ __forceinline__ void geo_prefetch(const SceneS& sc, const SampleSrc& src, const int* __restrict__ list, int count, int tile,
+                                             int q4, int h, int lane, uint32_t* __restrict__ fb, int parity, GeoPre& pre) {
+  constexpr int FA = tc_l0_fa(NK);
+  const int g = lane / 3;
+  const int v = lane - 3 * g;
+  const int si = tile * SPT + q4 * SPW + min(g, SPW - 1);
+  pre.id = list[max(min(si, count - 1), 0)];
+  float d[3];
+  fetch_sample(src, pre.id, pre.p, d);
+  const Proj q = project_s(sc, v, pre.p);
+  const Taps t64 = make_taps(q.u, q.v, sc.f64.W, sc.f64.H);
+  if (h == 0) {
+#pragma unroll
+    for (int gq = 0; gq < FA / 4; ++gq) {
+      float f[4];
+      gather_f32<1>(sc.f64, v, t64, gq, f);
+      fb[(2 * gq) * 128] = tc::pack_h2(f[0], f[1]);
+      fb[(2 * gq + 1) * 128] = tc::pack_h2(f[2], f[3]);
+    }
+  } else {
+#pragma unroll
+    for (int gq = FA / 4; gq < 16; ++gq) {
+      float f[4];
+      gather_f32<1>(sc.f64, v, t64, gq, f);
+      fb[(2 * gq) * 128] = tc::pack_h2(f[0], f[1]);
+      fb[(2 * gq + 1) * 128] = tc::pack_h2(f[2], f[3]);
+    }
+    const Taps t8 = make_taps(q.u, q.v, sc.f8.W, sc.f8.H);
+    float g8[8];
+    gather_f32<2>(sc.f8, v, t8, 0, g8);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fb[(32 + 4 * parity + i) * 128] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
+  }
+}
+
+// One tile of the geometry pass.  PREF: `pre` holds this tile's sample on entry (its gathers are staged in `fb`) and the next
+// tile's on exit, `nid` the sample id of the next tile on entry and of the tile after that (`next2_tile`) on exit;
+// `next_tile` < 0: nothing to prefetch.
+template <int NK, bool PREF>
 __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restrict__ wp2, GeoXch* __restrict__ xch,
-                                         const SampleSrc& src, const int* __restrict__ list, int count, int tile, GeoCtx& cx,
+                                         const SampleSrc& src, const int* __restrict__ list, int count, int tile, int next_tile,
+                                         int next2_tile, int& nid, uint32_t* __restrict__ fb, int parity, GeoPre& pre, GeoCtx& cx,
                                          int q4, int h, int lane, int bar_id, int query_mode, float* __restrict__ out5,
                                          uint4* __restrict__ lat_out, int2* __restrict__ list2, int* __restrict__ count2) {
   constexpr int NP = NK / 2, PA = tc_l0_pa(NK), FA = tc_l0_fa(NK);
@@ -261,9 +342,15 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   const int v = lane - 3 * g;           // lanes 30,31 replay views 0,1 of the warp's last sample (results unused)
   const int si = tile * SPT + q4 * SPW + min(g, SPW - 1);
   const bool writer = (h == 0) && (lane < 3 * SPW) && (v == 0) && (si < count);
-  const int id = list[min(si, count - 1)];
-  float p[3], d[3];
-  fetch_sample(src, id, p, d);
+  int id;
+  float p[3];
+  if (PREF) {
+    id = pre.id; p[0] = pre.p[0]; p[1] = pre.p[1]; p[2] = pre.p[2];
+  } else {
+    float d[3];
+    id = list[min(si, count - 1)];
+    fetch_sample(src, id, p, d);
+  }
   const Proj q = project_s(sc, v, p);
   const float bw = boundary_weight_fast(q);
   const float pw = bw / (gsum(cx, bw) + 1e-6f);  // reference src/model.py:750-759 (mask == 1 for shaded samples)
@@ -277,16 +364,22 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
       c[1] = E[4] * p[0] + E[5] * p[1] + E[6] * p[2] + E[7];
       c[2] = E[8] * p[0] + E[9] * p[1] + E[10] * p[2] + E[11];
     }
-    const Taps t64 = make_taps(q.u, q.v, sc.f64.W, sc.f64.H);
+    Taps t64;
+    if (!PREF) t64 = make_taps(q.u, q.v, sc.f64.W, sc.f64.H);
     if (h == 0) {
       constexpr int N0 = 7 * PA + FA / 2;
       uint32_t a[N0];
+      if (PREF) {
 #pragma unroll
-      for (int gq = 0; gq < FA / 4; ++gq) {
-        float f[4];
-        gather_f32<1>(sc.f64, v, t64, gq, f);
-        a[7 * PA + 2 * gq] = tc::pack_h2(f[0], f[1]);
-        a[7 * PA + 2 * gq + 1] = tc::pack_h2(f[2], f[3]);
+        for (int i = 0; i < FA / 2; ++i) a[7 * PA + i] = fb[i * 128];
+      } else {
+#pragma unroll
+        for (int gq = 0; gq < FA / 4; ++gq) {
+          float f[4];
+          gather_f32<1>(sc.f64, v, t64, gq, f);
+          a[7 * PA + 2 * gq] = tc::pack_h2(f[0], f[1]);
+          a[7 * PA + 2 * gq + 1] = tc::pack_h2(f[2], f[3]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < PA; ++j) {
@@ -302,12 +395,17 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
       constexpr int NE = 7 * (NP - PA), NF = (64 - FA) / 2;
       constexpr int N1 = tc_k0p(NK) / 2 - C1;
       uint32_t a[N1];
+      if (PREF) {
 #pragma unroll
-      for (int gq = 0; gq < (64 - FA) / 4; ++gq) {
-        float f[4];
-        gather_f32<1>(sc.f64, v, t64, FA / 4 + gq, f);
-        a[NE + 2 * gq] = tc::pack_h2(f[0], f[1]);
-        a[NE + 2 * gq + 1] = tc::pack_h2(f[2], f[3]);
+        for (int i = 0; i < NF; ++i) a[NE + i] = fb[(FA / 2 + i) * 128];
+      } else {
+#pragma unroll
+        for (int gq = 0; gq < (64 - FA) / 4; ++gq) {
+          float f[4];
+          gather_f32<1>(sc.f64, v, t64, FA / 4 + gq, f);
+          a[NE + 2 * gq] = tc::pack_h2(f[0], f[1]);
+          a[NE + 2 * gq + 1] = tc::pack_h2(f[2], f[3]);
+        }
       }
 #pragma unroll
       for (int j = PA; j < NP; ++j) {
@@ -323,33 +421,91 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
       st_cols<N1, C1>(A + C1, a);
     }
   }
+  // ---- staging of this row's NEXT tile, spread over the six accumulator waits of this tile: every global load is issued
+  //      just before a stage is signalled and consumed right after that stage's accumulator arrived, so its latency hides
+  //      behind the tensor core instead of stalling the row (each thread stages only the words it will read itself).
+  const bool pf = PREF && next_tile >= 0;
+  constexpr int FG = FA / 4;                 // feat64 float4 groups owned by thread 0 (thread 1: [FG, 16) + the two feat8 groups)
+  static_assert(!PREF || FG == 10, "the window plan below assumes 10 | 6 feat64 groups per thread (18 keypoints)");
+  float4 pr[2][4];
+  float pwt[4];
+  float nu = 0.0f, nv = 0.0f;
+  // windows 1..5: feature gathers of the next tile, two float4 groups each (thread 0: feat64 groups 2w, 2w+1; thread 1: feat64
+  // groups 10+2w, 11+2w for w < 3, then the two feat8 groups)
+  auto win_issue = [&](int w) {
+    if (h == 1 && w == 4) return;
+    const bool f8w = (h == 1) && (w == 3);
+    const MapDesc& m = f8w ? sc.f8 : sc.f64;
+    const Taps t = make_taps(nu, nv, m.W, m.H);
+    pwt[0] = t.w00; pwt[1] = t.w01; pwt[2] = t.w10; pwt[3] = t.w11;
+    taps_issue<2>(m, v, t, f8w ? 0 : (h == 0 ? 2 * w : FG + 2 * w), pr);
+  };
+  auto win_stage = [&](int w) {
+    if (h == 1 && w == 4) return;
+    taps_stage<2>(pwt, pr, fb, h == 0 ? 4 * w : (w == 3 ? 32 + 4 * (parity ^ 1) : 2 * FG + 4 * w));
+  };
   geo_signal(cx, lane);
+  // window 0: position of the next tile's sample (its id was fetched during the previous tile; reference src/model.py:1057:
+  // p = cam_pos + dir * z, or an explicit query point) and the id of the tile after that
+  float nl[7];
+  int nid2 = 0;
+  if (pf) {
+    if (src.mode == 0) {
+      const int r = nid / src.S;
+      nl[0] = __ldg(src.z + nid);
+      nl[1] = __ldg(src.ray_d + 3 * r); nl[2] = __ldg(src.ray_d + 3 * r + 1); nl[3] = __ldg(src.ray_d + 3 * r + 2);
+      nl[4] = __ldg(src.o); nl[5] = __ldg(src.o + 1); nl[6] = __ldg(src.o + 2);
+    } else {
+      nl[0] = __ldg(src.pts + 3ll * nid); nl[1] = __ldg(src.pts + 3ll * nid + 1); nl[2] = __ldg(src.pts + 3ll * nid + 2);
+    }
+    if (next2_tile >= 0) nid2 = __ldg(list + max(min(next2_tile * SPT + q4 * SPW + min(g, SPW - 1), count - 1), 0));
+  }
   const uint32_t dh = A + 128u + 64u * (uint32_t)h, ah = A + 32u * (uint32_t)h;
-  // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720); the h = 0 thread also writes the bias / feat8 chunk
+  // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720); thread 0 writes the bias chunk, thread 1 the feat8 | bias chunk
   geo_wait(cx);
+  if (pf) {
+    pre.id = nid;
+    if (src.mode == 0) { pre.p[0] = nl[4] + nl[1] * nl[0]; pre.p[1] = nl[5] + nl[2] * nl[0]; pre.p[2] = nl[6] + nl[3] * nl[0]; }
+    else { pre.p[0] = nl[0]; pre.p[1] = nl[1]; pre.p[2] = nl[2]; }
+    const Proj nq = project_s(sc, v, pre.p);
+    nu = nq.u; nv = nq.v;
+    nid = nid2;
+  }
   geo_epi_sp(dh, ah, false);
   if (h == 0) {
     const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     tc::tmem_st8(A + 64, b);
   }
   geo_signal(cx, lane);
+  if (pf) win_issue(0);
   geo_wait(cx);
+  if (pf) win_stage(0);
   geo_epi_sp(dh, ah, false);
-  if (h == 0) {
-    const Taps t8 = make_taps(q.u, q.v, sc.f8.W, sc.f8.H);
-    float g8[8];
-    gather_f32<2>(sc.f8, v, t8, 0, g8);
-    const uint32_t b[8] = {tc::pack_h2(g8[0], g8[1]), tc::pack_h2(g8[2], g8[3]), tc::pack_h2(g8[4], g8[5]), tc::pack_h2(g8[6], g8[7]),
-                           H2_ONE, 0u, 0u, 0u};
+  if (h == 1) {
+    uint32_t b[8] = {0u, 0u, 0u, 0u, H2_ONE, 0u, 0u, 0u};
+    if (PREF) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = fb[(32 + 4 * parity + i) * 128];
+    } else {
+      const Taps t8 = make_taps(q.u, q.v, sc.f8.W, sc.f8.H);
+      float g8[8];
+      gather_f32<2>(sc.f8, v, t8, 0, g8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
+    }
     tc::tmem_st8(A + 64, b);
   }
   geo_signal(cx, lane);
+  if (pf) win_issue(1);
   geo_wait(cx);
+  if (pf) win_stage(1);
   geo_epi_sp(dh, ah, h == 1);
   geo_signal(cx, lane);
+  if (pf) win_issue(2);
   // ---- view pooling: weighted mean || variance over the 3 lanes of the group (src/utils.py:722-748); this thread owns 32
   //      of the 64 feature columns; the density tail's inputs are kept to two fp16 terms (hi | lo)
   geo_wait(cx);
+  if (pf) win_stage(2);
   {
     uint32_t r[32];
     tc::tmem_ld32(A + 192u + 32u * (uint32_t)h, r);
@@ -378,8 +534,10 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     }
   }
   geo_signal(cx, lane);
+  if (pf) win_issue(3);
   // ---- P0 (softplus, two fp16 terms out) | compress (linear; this thread keeps 12 of the 24 latent values as 6 fp16 pairs)
   geo_wait(cx);
+  if (pf) win_stage(3);
   uint32_t latp[6];
   {
     uint32_t rc[16], r[32];
@@ -403,8 +561,10 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     }
   }
   geo_signal(cx, lane);
+  if (pf) win_issue(4);
   // ---- P1 (softplus) then the 64->2 density head in fp32 on the CUDA cores: each thread a partial dot over its 32 columns
   geo_wait(cx);
+  if (pf) win_stage(4);
   float g0 = 0.0f, rad = 0.0f;
   {
     uint32_t r[32];
@@ -658,7 +818,8 @@ constexpr uint32_t A_IN_R1 = 0xA9Au;
 // (a stage's half tile sits at plan offset / 2; `lo_delta` = descriptor distance of the W_lo halves).  Per K chunk of 16 the
 // descriptor's start address advances by two core-matrix columns (2 * LBO).  Order: A_hi x W_hi, [A_hi x W_lo], [A_lo x W_hi].
 template <int NK, int STAGE>
-__device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint32_t lo_delta, bool two_term, uint32_t el) {
+__device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint32_t lo_delta, int lo_mask, uint32_t el) {
+  const bool two_term = (lo_mask >> STAGE) & 1, act_lo = STAGE >= 4 && ((lo_mask >> (STAGE + 2)) & 1);
   constexpr TcPlan plan = make_tc_plan(NK);
   constexpr int Kp = plan.st[STAGE].Kp, Np = plan.st[STAGE].Np;
   constexpr uint32_t lbo = (uint32_t)(Np / 16) * 128u;   // half tile: Np/2 rows -> (Np/2)/8 core matrices per K column of 8
@@ -679,7 +840,7 @@ __device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint3
     for (int j = 0; j < NCH; ++j)
       tc::mma_ts2_el(d_tm, slot_tm + (uint32_t)(j < NACT ? 8 * j : BIASCOL), b0 + lo_delta + (uint32_t)j * step, dhi, idesc, 1u, el);
   }
-  if (STAGE >= 4) {
+  if (act_lo) {
 #pragma unroll
     for (int j = 0; j < NACT; ++j)
       tc::mma_ts2_el(d_tm, slot_tm + (uint32_t)(LOCOL + 8 * j), b0 + (uint32_t)j * step, dhi, idesc, 1u, el);
@@ -741,7 +902,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEO_THREADS, 1)
 shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
                  int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
                  int query_mode, float* __restrict__ out5, uint4* __restrict__ lat_out, int2* __restrict__ list2,
-                 int* __restrict__ count2, int issue_branch) {
+                 int* __restrict__ count2, int issue_branch, int relaxed_arrive) {
   extern __shared__ __align__(1024) uint8_t wsm[];
   // barriers: [0] weights | per slot s: [1+2s] a_ready (one arrival per row warp of the pair = 16; only the leader's copy is
   //           used), [2+2s] acc_ready (one multicast commit per stage, each CTA waits on its own copy)
@@ -752,6 +913,7 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
   __shared__ __align__(16) GeoXch xch[NSLOT][128];
   constexpr TcPlan plan = make_tc_plan(NK);
   constexpr uint32_t WBYTES = plan.st[GEO_NSTAGE].off;   // per CTA: half of W_hi + half of W_lo of stages 0..5
+  constexpr bool PREF = geo_pref(NK);                    // gather staging buffer behind the weights
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const uint32_t rank = tc::cluster_ctarank();
   const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
@@ -796,12 +958,12 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
             const uint32_t lod = (WBYTES / 2u) >> 4;
             auto issue = [&](uint32_t e) {
               switch (stage[s]) {
-                case 0: geo_issue<NK, 0>(stm, wlo0, lod, two_term != 0, e); break;
-                case 1: geo_issue<NK, 1>(stm, wlo0, lod, two_term != 0, e); break;
-                case 2: geo_issue<NK, 2>(stm, wlo0, lod, two_term != 0, e); break;
-                case 3: geo_issue<NK, 3>(stm, wlo0, lod, two_term != 0, e); break;
-                case 4: geo_issue<NK, 4>(stm, wlo0, lod, two_term != 0, e); break;
-                default: geo_issue<NK, 5>(stm, wlo0, lod, two_term != 0, e); break;
+                case 0: geo_issue<NK, 0>(stm, wlo0, lod, two_term, e); break;
+                case 1: geo_issue<NK, 1>(stm, wlo0, lod, two_term, e); break;
+                case 2: geo_issue<NK, 2>(stm, wlo0, lod, two_term, e); break;
+                case 3: geo_issue<NK, 3>(stm, wlo0, lod, two_term, e); break;
+                case 4: geo_issue<NK, 4>(stm, wlo0, lod, two_term, e); break;
+                default: geo_issue<NK, 5>(stm, wlo0, lod, two_term, e); break;
               }
               tc::mma_commit2_el(&bars[2 + 2 * s], e);
             };
@@ -825,14 +987,28 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl) : "r"(tc::smem_u32(&bars[1 + 2 * slot])), "r"(0u));
     cx.acc_ready = &bars[2 + 2 * slot];
     cx.ph = 0;
+    cx.relaxed = relaxed_arrive;
     const int gb = 3 * (lane / 3);
     cx.l1 = (gb + (lane - gb + 1) % 3) & 31;
     cx.l2 = (gb + (lane - gb + 2) % 3) & 31;
     const int bar_id = 1 + slot * 4 + q4;
-    for (int P = cl * NSLOT + slot; 2 * P < ntiles; P += ncl * NSLOT) {
+    uint32_t* fb = reinterpret_cast<uint32_t*>(wsm + WBYTES) + slot * (GEO_FW * 128) + 32 * q4 + lane;   // this row's staging column
+    GeoPre pre;
+    int parity = 0;
+    int P = cl * NSLOT + slot;
+    int nid = 0;
+    auto id_of_tile = [&](int tile) { return list[max(min(tile * SPT + q4 * SPW + min(lane / 3, SPW - 1), count - 1), 0)]; };
+    if (PREF && 2 * P < ntiles) {
+      geo_prefetch<NK>(scs, src, list, count, 2 * P + (int)rank, q4, h, lane, fb, 0, pre);
+      nid = id_of_tile(2 * (P + ncl * NSLOT) + (int)rank);
+    }
+    for (; 2 * P < ntiles; P += ncl * NSLOT) {
       // a tile index past the end is a ghost tile: it replays the last sample, takes part in every barrier, writes nothing
-      geo_tile<NK>(scs, wp2, xch[slot], src, list, count, 2 * P + (int)rank, cx, q4, h, lane, bar_id, query_mode, out5, lat_out,
-                   list2, count2);
+      const int Pn = P + ncl * NSLOT, Pn2 = Pn + ncl * NSLOT;
+      geo_tile<NK, PREF>(scs, wp2, xch[slot], src, list, count, 2 * P + (int)rank, 2 * Pn < ntiles ? 2 * Pn + (int)rank : -1,
+                         2 * Pn2 < ntiles ? 2 * Pn2 + (int)rank : -1, nid, fb, parity, pre, cx, q4, h, lane, bar_id, query_mode, out5,
+                         lat_out, list2, count2);
+      parity ^= 1;
     }
   }
   tc::fence_before_sync();
@@ -933,7 +1109,7 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
                                   const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
                                   uint4* lat, int2* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
   constexpr TcPlan plan = make_tc_plan(NK);
-  const size_t smem_geo = plan.st[GEO_NSTAGE].off;
+  const size_t smem_geo = plan.st[GEO_NSTAGE].off + (geo_pref(NK) ? (size_t)NSLOT * GEO_FW * 128 * 4 : 0);
   const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
   static bool attr = false;
   if (!attr) {
@@ -947,9 +1123,13 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   long long pairs = (max_tiles + 2 * NSLOT - 1) / (2 * NSLOT);   // clusters that can have work
   const int max_clusters = num_sms / 2;
   int grid = 2 * (int)(pairs < 1 ? 1 : (pairs > max_clusters ? max_clusters : pairs));
+  static const int relaxed_arrive = [] { const char* e = getenv("KPN_RELAXED_ARRIVE"); return e && e[0] == '0' ? 0 : 1; }();
   static const int issue_branch = [] { const char* e = getenv("KPN_ISSUE_BRANCH"); return e && e[0] == '1' ? 1 : 0; }();
+  // which stages get the W_lo pass (bits 0..5) and the A_lo pass (bits 6, 7 for stages 4, 5); KPN_LO_MASK overrides (experiments)
+  static const int lo_env = [] { const char* e = getenv("KPN_LO_MASK"); return e ? (int)strtol(e, nullptr, 0) : -1; }();
+  two_term = two_term ? (lo_env >= 0 ? lo_env : 0xFF) : 0xC0;
   shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, out5, lat, list2,
-                                                           count2, issue_branch);
+                                                           count2, issue_branch, relaxed_arrive);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   long long g = (max_tiles + CSLOT - 1) / CSLOT;
