@@ -100,28 +100,26 @@ __device__ __forceinline__ float boundary_weight_fast(const Proj& q) {
 
 struct RowCtx {
   uint32_t R0, R1;      // TMEM addresses (lane field already set) of the slot's two column regions
-  uint64_t* a_ready;    // row threads -> MMA thread : "layer input is in TMEM"   (count 128)
-  uint32_t a_ready_cl;  // != 0: cluster-mapped shared address of the LEADER CTA's a_ready (CTA-pair kernel, count 256)
-  uint64_t* acc_ready;  // MMA thread -> row threads : "accumulator is complete"  (tcgen05.commit)
+  uint64_t* a_ready;    // row warps -> MMA issuer : "layer input is in TMEM"   (one arrival per row warp)
+  uint64_t* acc_ready;  // MMA issuer -> row threads : "accumulator is complete"  (tcgen05.commit)
   uint32_t ph;          // parity of acc_ready this thread waits on next
   int gb;               // first lane of this row's 3-view group
   int l1, l2;           // the other two lanes of the group
-  unsigned long long* tim;  // optional debug timing accumulators (only one recording thread per CTA slot 0)
-  int st, st0, st1;     // stage counter for the timing, cycling in [st0, st1)
 };
 
+// The activation tile lives in tensor memory: tcgen05.wait::st + tcgen05.fence::before_thread_sync order it, so the arrive
+// itself carries no release (a release would also drain the thread's unrelated global loads).
 __device__ __forceinline__ void signal_a(RowCtx& c) {
   tc::wait_st();
   tc::fence_before_sync();
-  if (c.a_ready_cl) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(c.a_ready_cl) : "memory");
-  else tc::mbar_arrive(c.a_ready);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(c.a_ready)) : "memory");
 }
 __device__ __forceinline__ void wait_acc(RowCtx& c) {
-  long long t0 = c.tim ? clock64() : 0;
   tc::mbar_wait(c.acc_ready, c.ph);
   c.ph ^= 1u;
   tc::fence_after_sync();
-  if (c.tim) { atomicAdd(&c.tim[c.st], (unsigned long long)(clock64() - t0)); c.st = c.st + 1 == c.st1 ? c.st0 : c.st + 1; }
 }
 __device__ __forceinline__ float gsum(const RowCtx& c, float x) {
   return x + __shfl_sync(FULL, x, c.l1) + __shfl_sync(FULL, x, c.l2);
@@ -214,19 +212,22 @@ __device__ __forceinline__ float gsum(const GeoCtx& c, float x) {
   return x + __shfl_sync(FULL, x, c.l1) + __shfl_sync(FULL, x, c.l2);
 }
 
-// softplus(beta=100) of two accumulators -> packed fp16 pair.  max(x,0) in fp32; the correction log1p(exp(-100|x|))/100 <= 0.00693
-// from ONE ex2 per element and a cubic in e = exp(-100|x|) evaluated on packed halves (max error of the polynomial 7e-7, of
-// the fp16 evaluation 7e-6: below the rounding of the fp16 result itself for every |x| > 0.004).
+// softplus(beta=100) of two accumulators -> packed fp16 pair, on packed halves throughout: x is rounded to fp16 first (the
+// result is an fp16 activation anyway), y = max(x,0) + e*g(e) with e = exp(-100|x|) from ONE ex2 per element and g a cubic
+// (max error of e*g(e) against log1p(e)/100: 7e-7; rms error of the fp16 pipeline = that of rounding the exact softplus).
 __device__ __forceinline__ uint32_t sp_pair(uint32_t a0, uint32_t a1) {
-  const float x0 = u2f(a0), x1 = u2f(a1);
-  const float e0 = ex2f(-100.0f * LOG2E * fabsf(x0)), e1 = ex2f(-100.0f * LOG2E * fabsf(x1));
-  const __half2 e = __floats2half2_rn(e0, e1);
+  const __half2 xh = __floats2half2_rn(u2f(a0), u2f(a1));
+  const uint32_t kt = 0xd882d882u;   // -144.25 = fp16(-100 * log2(e))
   const uint32_t k3 = 0x90d090d0u, k2 = 0x189f189fu, k1 = 0x9cd39cd3u, k0 = 0x211b211bu;   // -5.875e-4, 2.2564e-3, -4.7112e-3, 9.9716e-3
-  __half2 pl = __hfma2(e, *reinterpret_cast<const __half2*>(&k3), *reinterpret_cast<const __half2*>(&k2));
-  pl = __hfma2(pl, e, *reinterpret_cast<const __half2*>(&k1));
-  pl = __hfma2(pl, e, *reinterpret_cast<const __half2*>(&k0));
-  pl = __hmul2(pl, e);
-  const __half2 y = __hadd2(__floats2half2_rn(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)), pl);
+  const __half2 t = __hmul2(__habs2(xh), *reinterpret_cast<const __half2*>(&kt));
+  uint32_t eu;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(eu) : "r"(*reinterpret_cast<const uint32_t*>(&t)));
+  const __half2 e = *reinterpret_cast<const __half2*>(&eu);
+  __half2 g = __hfma2(e, *reinterpret_cast<const __half2*>(&k3), *reinterpret_cast<const __half2*>(&k2));
+  g = __hfma2(g, e, *reinterpret_cast<const __half2*>(&k1));
+  g = __hfma2(g, e, *reinterpret_cast<const __half2*>(&k0));
+  const uint32_t zero = 0u;
+  const __half2 y = __hfma2(g, e, __hmax2(xh, *reinterpret_cast<const __half2*>(&zero)));
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
@@ -847,27 +848,21 @@ __device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint3
   }
 }
 
-// MMAs of one stage on resident weights.  `region` = width of the slot's R0/R1 regions, `wbase` = shared address the
-// stage offsets of `plan` are relative to, minus `off0` (first stage resident in this kernel).
-__device__ __forceinline__ void issue_stage(uint32_t slot_tm, uint32_t region, uint32_t wsmem, uint32_t off0, const TcPlan& plan,
-                                            int stage) {
-  const uint32_t a_r1 = (A_IN_R1 >> stage) & 1u;
-  const uint32_t a_tm = slot_tm + (a_r1 ? region : 0u), d_tm = slot_tm + (a_r1 ? 0u : region);
-  const int Kp = plan.st[stage].Kp, Np = plan.st[stage].Np;
-  const uint32_t lbo = (uint32_t)(Np / 8) * 128u;
-  const uint32_t idesc = tc::make_idesc_f16(128, Np);
-  const uint32_t b0 = wsmem + plan.st[stage].off - off0;
-  for (int j = 0; j < Kp / 16; ++j) {
-    uint64_t bd = tc::make_smem_desc(b0 + (uint32_t)j * 2u * lbo, lbo, 128u);
-    tc::mma_ts(d_tm, a_tm + (uint32_t)j * 8u, bd, idesc, j > 0 ? 1u : 0u);
-  }
-  // density tail (stages 4, 5): the activations come as hi | lo, the lo half sits Kp/2 columns further
-  if (stage == 4 || stage == 5) {
-    for (int j = 0; j < Kp / 16; ++j) {
-      uint64_t bd = tc::make_smem_desc(b0 + (uint32_t)j * 2u * lbo, lbo, 128u);
-      tc::mma_ts(d_tm, a_tm + (uint32_t)(Kp / 2) + (uint32_t)j * 8u, bd, idesc, 1u);
-    }
-  }
+// MMAs of one colour stage on resident weights, issued warp-converged like geo_issue.  `wlo0`: descriptor low word of the
+// shared-memory base the colour stages' plan offsets are relative to (minus the first colour stage's offset).
+template <int NK, int STAGE>
+__device__ __forceinline__ void col_issue(uint32_t slot_tm, uint32_t wlo0, uint32_t el) {
+  constexpr TcPlan plan = make_tc_plan(NK);
+  constexpr int Kp = plan.st[STAGE].Kp, Np = plan.st[STAGE].Np;
+  constexpr uint32_t lbo = (uint32_t)(Np / 8) * 128u;
+  constexpr uint32_t idesc = tc::make_idesc_f16(128, Np);
+  constexpr uint32_t dhi = (128u >> 4) | (1u << 14);
+  constexpr uint32_t step = (2u * lbo) >> 4;
+  constexpr uint32_t a_r1 = (A_IN_R1 >> STAGE) & 1u;
+  const uint32_t a_tm = slot_tm + (a_r1 ? 64u : 0u), d_tm = slot_tm + (a_r1 ? 0u : 64u);
+  const uint32_t b0 = wlo0 + ((plan.st[STAGE].off - plan.st[GEO_NSTAGE].off) >> 4) + ((lbo >> 4) << 16);
+#pragma unroll
+  for (int j = 0; j < Kp / 16; ++j) tc::mma_ts_el(d_tm, a_tm + (uint32_t)j * 8u, b0 + (uint32_t)j * step, dhi, idesc, j > 0 ? 1u : 0u, el);
 }
 
 __device__ __forceinline__ void stage_scene(SceneS& scs, const DevScene& g, int NK, int t, int nthreads) {
@@ -1024,7 +1019,7 @@ template <int NK>
 __global__ void __launch_bounds__(TCC_THREADS, 1)
 shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
                    SampleSrc src, const int2* __restrict__ list2, const int* __restrict__ count_ptr,
-                   const uint4* __restrict__ lat_in, float* __restrict__ out5, unsigned long long* __restrict__ timing) {
+                   const uint4* __restrict__ lat_in, float* __restrict__ out5) {
   extern __shared__ __align__(1024) uint8_t wsm[];
   __shared__ uint64_t bars[1 + 2 * CSLOT];   // [0] weights | per slot: a_ready, acc_ready
   __shared__ uint32_t tmem_base_s;
@@ -1039,7 +1034,7 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
   if (warp == ISSUER) tc::tmem_alloc(&tmem_base_s, 512);
   if (t == 0) {
     tc::mbar_init(&bars[0], 1);
-    for (int s = 0; s < CSLOT; ++s) { tc::mbar_init(&bars[1 + 2 * s], ROW_WARPS * 32); tc::mbar_init(&bars[2 + 2 * s], 1); }
+    for (int s = 0; s < CSLOT; ++s) { tc::mbar_init(&bars[1 + 2 * s], ROW_WARPS); tc::mbar_init(&bars[2 + 2 * s], 1); }
     tc::fence_mbar_init();
   }
   tc::fence_before_sync();
@@ -1052,19 +1047,29 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
     return n;
   };
   if (warp == ISSUER) {
-    if (lane == 0 && ntiles > 0) {
-      load_weights(wsm, wblob + OFF0, WBYTES, &bars[0]);
-      const uint32_t wsmem = tc::smem_u32(wsm);
+    if (ntiles > 0) {      // the whole warp runs the loop, one elected lane issues
+      if (lane == 0) load_weights(wsm, wblob + OFF0, WBYTES, &bars[0]);
+      __syncwarp();
+      const uint32_t el = tc::elect_one();
+      const uint32_t wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu;
       int remaining[CSLOT], stage[CSLOT], left = 0;
       uint32_t par[CSLOT];
       for (int s = 0; s < CSLOT; ++s) { remaining[s] = tiles_of_slot(s) * COL_NSTAGE; stage[s] = 0; par[s] = 0; left += remaining[s]; }
       while (left > 0) {
 #pragma unroll
         for (int s = 0; s < CSLOT; ++s) {
-          if (remaining[s] > 0 && tc::mbar_test_wait(&bars[1 + 2 * s], par[s])) {
+          if (remaining[s] > 0 && __all_sync(FULL, tc::mbar_test_wait(&bars[1 + 2 * s], par[s]))) {
             tc::fence_after_sync();
-            issue_stage(tbase + (uint32_t)s * 128u, 64u, wsmem, OFF0, plan, GEO_NSTAGE + stage[s]);
-            tc::mma_commit(&bars[2 + 2 * s]);
+            const uint32_t stm = tbase + (uint32_t)s * 128u;
+            switch (stage[s]) {
+              case 0: col_issue<NK, 6>(stm, wlo0, el); break;
+              case 1: col_issue<NK, 7>(stm, wlo0, el); break;
+              case 2: col_issue<NK, 8>(stm, wlo0, el); break;
+              case 3: col_issue<NK, 9>(stm, wlo0, el); break;
+              case 4: col_issue<NK, 10>(stm, wlo0, el); break;
+              default: col_issue<NK, 11>(stm, wlo0, el); break;
+            }
+            tc::mma_commit_el(&bars[2 + 2 * s], el);
             par[s] ^= 1u;
             stage[s] = stage[s] + 1 == COL_NSTAGE ? 0 : stage[s] + 1;
             --remaining[s];
@@ -1079,19 +1084,13 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
     const uint32_t tm = tbase + (uint32_t)slot * 128u + ((uint32_t)(roww * 32) << 16);
     cx.R0 = tm; cx.R1 = tm + 64u;
     cx.a_ready = &bars[1 + 2 * slot];
-    cx.a_ready_cl = 0;
     cx.acc_ready = &bars[2 + 2 * slot];
     cx.ph = 0;
     cx.gb = 3 * (lane / 3);
     cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
     cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
-    cx.tim = (timing != nullptr && warp == 0 && lane == 0) ? timing : nullptr;
-    cx.st = GEO_NSTAGE; cx.st0 = GEO_NSTAGE; cx.st1 = GEO_NSTAGE + COL_NSTAGE;
-    for (int tile = blockIdx.x * CSLOT + slot; tile < ntiles; tile += gridDim.x * CSLOT) {
-      long long t0 = cx.tim ? clock64() : 0;
+    for (int tile = blockIdx.x * CSLOT + slot; tile < ntiles; tile += gridDim.x * CSLOT)
       color_tile(scs, C, src, list2, count, tile, cx, roww, lane, lat_in, out5);
-      if (cx.tim) { atomicAdd(&cx.tim[14], (unsigned long long)(clock64() - t0)); atomicAdd(&cx.tim[15], 1ull); }
-    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -1134,7 +1133,7 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   if (e != cudaSuccess) return e;
   long long g = (max_tiles + CSLOT - 1) / CSLOT;
   grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
-  shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, count2, lat, out5, timing);
+  shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, count2, lat, out5);
   return cudaGetLastError();
 }
 

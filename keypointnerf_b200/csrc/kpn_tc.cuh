@@ -220,6 +220,21 @@ __device__ __forceinline__ void mma_ts2_el(uint32_t d_tmem, uint32_t a_tmem, uin
       "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(el)
       : "memory");
 }
+// single-CTA variants of the warp-converged issue
+__device__ __forceinline__ void mma_ts_el(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                          uint32_t accumulate, uint32_t el) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(el)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_el(uint64_t* bar, uint32_t el) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(el)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit2_el(uint64_t* bar, uint32_t el) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
