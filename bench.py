@@ -49,6 +49,18 @@ def flop_per_sample(n_kpt: int, n_views: int) -> int:
     return 2 * (n_views * (geo + ibr) + pooled)
 
 
+def ncu_traffic():
+    """DRAM bytes per shading launch pair (geometry + colour kernel) from the latest committed ncu capture (profiles/*_traffic.json,
+    written by tools/summarize_profile.py); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    tot = sum(k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0) for k in d["kernels"].values())
+    return tot, os.path.basename(files[-1])
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -245,12 +257,15 @@ def main():
     launches = st["kernel_launches"] - launches0
 
     # end to end through the reference-facing API, host buffers in / host buffers out
-    for _ in range(2):
+    for _ in range(3):
         step_e2e()
     barrier()
+    e2e_each = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = step_e2e()
+        t1 = time.perf_counter()
+        out = step_e2e()      # returns host tensors: the call itself waits for the device-to-host copies
+        e2e_each.append((time.perf_counter() - t1) * 1e3)
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -266,8 +281,11 @@ def main():
     valid_per_step = st["samples_valid"]
     shade_ms = st["shade_ms"]
     ach = (fps * valid_per_step * args.steps) / (shade_ms * 1e-3) / 1e12 if shade_ms > 0 else None
-    roofline = {"bound": "tensor", "kernel": "shade (per-sample gather+encode+MLPs)", "achieved": ach,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": (ach / pk["tflops"]) if ach else None, "traffic": None,
+    traffic, traffic_src = ncu_traffic()
+    roofline = {"bound": "tensor", "kernel": "shade_geo_kernel + shade_color_kernel (per-sample gather+encode+MLPs; geometry is ~85% of it)",
+                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": (ach / pk["tflops"]) if ach else None,
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch pair (one chunk of 32768 rays), ncu --set full",
+                "traffic_source": traffic_src,
                 "peak_source": pk["source"], "flop_per_sample": fps, "valid_samples_per_step": valid_per_step,
                 "valid_frac": valid_per_step / float(SIZE * SIZE * S_C), "shade_ms_per_step": shade_ms / args.steps,
                 "shade_launches_per_step": st["shade_launches"] / args.steps,
@@ -289,7 +307,8 @@ def main():
                            "l2": "flushed between timed iterations (256 MiB write)", "engine": args.engine,
                            "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
                 "clocks": clocks,
-                "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_each": [round(x, 2) for x in e2e_each]},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

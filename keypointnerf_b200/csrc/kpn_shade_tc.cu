@@ -189,6 +189,13 @@ struct GeoCtx {
   uint64_t* acc_ready;  // this CTA's copy of the slot's accumulator barrier
   uint32_t ph;
   int l1, l2;           // the other two lanes of this row's 3-view group
+  // the slot's MMA issuer (one row warp of the pair's leader CTA; there is no dedicated control warp, so that 16 warps keep
+  // 128 registers per thread): waits for the slot's a_ready phase, issues the stage's MMAs, commits to acc_ready
+  int issuer;
+  uint64_t* a_ready;    // leader CTA's barrier (local address, issuer only)
+  uint32_t pha;
+  uint32_t slot_tm, wlo0, lod, el;
+  int lo_mask;
   int relaxed;          // arrive without release semantics (default; KPN_RELAXED_ARRIVE=0 reverts): the activation tile lives in
                         // tensor memory and is ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync; a release
                         // would additionally drain the row's in-flight prefetch loads (measured: 40.4 -> 35.4 ms/frame)
@@ -207,6 +214,19 @@ __device__ __forceinline__ void geo_wait(GeoCtx& c) {
   tc::mbar_wait(c.acc_ready, c.ph);
   c.ph ^= 1u;
   tc::fence_after_sync();
+}
+template <int NK, int STAGE>
+__device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint32_t lo_delta, int lo_mask, uint32_t el);
+// issuer warp only: once every row warp of the pair has signalled this stage's input, issue its MMAs
+template <int NK, int STAGE>
+__device__ __forceinline__ void geo_mma(GeoCtx& c) {
+  if (c.issuer) {
+    tc::mbar_wait(c.a_ready, c.pha);
+    c.pha ^= 1u;
+    tc::fence_after_sync();
+    geo_issue<NK, STAGE>(c.slot_tm, c.wlo0, c.lod, c.lo_mask, c.el);
+    tc::mma_commit2_el(c.acc_ready, c.el);
+  }
 }
 __device__ __forceinline__ float gsum(const GeoCtx& c, float x) {
   return x + __shfl_sync(FULL, x, c.l1) + __shfl_sync(FULL, x, c.l2);
@@ -463,6 +483,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   }
   const uint32_t dh = A + 128u + 64u * (uint32_t)h, ah = A + 32u * (uint32_t)h;
   // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720); thread 0 writes the bias chunk, thread 1 the feat8 | bias chunk
+  geo_mma<NK, 0>(cx);
   geo_wait(cx);
   if (pf) {
     pre.id = nid;
@@ -479,6 +500,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   }
   geo_signal(cx, lane);
   if (pf) win_issue(0);
+  geo_mma<NK, 1>(cx);
   geo_wait(cx);
   if (pf) win_stage(0);
   geo_epi_sp(dh, ah, false);
@@ -498,6 +520,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   }
   geo_signal(cx, lane);
   if (pf) win_issue(1);
+  geo_mma<NK, 2>(cx);
   geo_wait(cx);
   if (pf) win_stage(1);
   geo_epi_sp(dh, ah, h == 1);
@@ -505,6 +528,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   if (pf) win_issue(2);
   // ---- view pooling: weighted mean || variance over the 3 lanes of the group (src/utils.py:722-748); this thread owns 32
   //      of the 64 feature columns; the density tail's inputs are kept to two fp16 terms (hi | lo)
+  geo_mma<NK, 3>(cx);
   geo_wait(cx);
   if (pf) win_stage(2);
   {
@@ -537,6 +561,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   geo_signal(cx, lane);
   if (pf) win_issue(3);
   // ---- P0 (softplus, two fp16 terms out) | compress (linear; this thread keeps 12 of the 24 latent values as 6 fp16 pairs)
+  geo_mma<NK, 4>(cx);
   geo_wait(cx);
   if (pf) win_stage(3);
   uint32_t latp[6];
@@ -564,6 +589,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   geo_signal(cx, lane);
   if (pf) win_issue(4);
   // ---- P1 (softplus) then the 64->2 density head in fp32 on the CUDA cores: each thread a partial dot over its 32 columns
+  geo_mma<NK, 5>(cx);
   geo_wait(cx);
   if (pf) win_stage(4);
   float g0 = 0.0f, rad = 0.0f;
@@ -890,14 +916,14 @@ __device__ __forceinline__ void load_weights(uint8_t* dst, const uint8_t* src, u
 // geometry + density kernel (CTA pairs; 16 row warps = 2 slots x 4 TMEM lane quarters x 2 column halves, + 1 control warp)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GEO_ROW_WARPS = 16;
-constexpr int GEO_THREADS = (GEO_ROW_WARPS + 1) * 32;   // 544
+constexpr int GEO_THREADS = GEO_ROW_WARPS * 32;         // 512: no control warp (see GeoCtx::issuer)
 
 template <int NK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEO_THREADS, 1)
 shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
                  int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
                  int query_mode, float* __restrict__ out5, uint4* __restrict__ lat_out, int2* __restrict__ list2,
-                 int* __restrict__ count2, int issue_branch, int relaxed_arrive) {
+                 int* __restrict__ count2, int relaxed_arrive) {
   extern __shared__ __align__(1024) uint8_t wsm[];
   // barriers: [0] weights | per slot s: [1+2s] a_ready (one arrival per row warp of the pair = 16; only the leader's copy is
   //           used), [2+2s] acc_ready (one multicast commit per stage, each CTA waits on its own copy)
@@ -917,71 +943,35 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
   stage_scene(scs, *scp, NK, t, GEO_THREADS);
   for (int i = t; i < 130; i += GEO_THREADS) wp2[i] = i < 64 ? C.w_p2[0][i] : i < 128 ? C.w_p2[1][i - 64] : C.b_p2[i - 128];
 
-  if (warp == GEO_ROW_WARPS) tc::tmem_alloc2(&tmem_base_s, 512);
+  if (warp == 0) tc::tmem_alloc2(&tmem_base_s, 512);
   if (t == 0) {
     tc::mbar_init(&bars[0], 1);
     for (int s = 0; s < NSLOT; ++s) { tc::mbar_init(&bars[1 + 2 * s], GEO_ROW_WARPS); tc::mbar_init(&bars[2 + 2 * s], 1); }
     tc::fence_mbar_init();
   }
   __syncthreads();
-  if (warp == GEO_ROW_WARPS && lane == 0) load_weights(wsm, wpair + (size_t)rank * WBYTES, WBYTES, &bars[0]);   // this CTA's half-blob
+  if (t == 0) load_weights(wsm, wpair + (size_t)rank * WBYTES, WBYTES, &bars[0]);   // this CTA's half-blob
   tc::fence_before_sync();
   __syncthreads();
   tc::cluster_sync_all();     // both CTAs: barriers initialised, TMEM allocated, weights resident
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
   // pair iteration i of slot s covers tiles 2*P and 2*P+1 with P = (i*ncl + cl)*NSLOT + s; this CTA takes tile 2*P + rank
-  auto iters_of_slot = [&](int s) {
-    int n = 0;
-    for (int P = cl * NSLOT + s; 2 * P < ntiles; P += ncl * NSLOT) ++n;
-    return n;
-  };
-
-  if (warp == GEO_ROW_WARPS) {
-    if (rank == 0 && ntiles > 0) {   // the pair's MMA issuer: the whole warp runs the loop, one elected lane issues
-      const uint32_t el = tc::elect_one();
-      const uint32_t wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu;
-      int remaining[NSLOT], stage[NSLOT];
-      uint32_t par[NSLOT];
-      for (int s = 0; s < NSLOT; ++s) { remaining[s] = iters_of_slot(s) * GEO_NSTAGE; stage[s] = 0; par[s] = 0; }
-      while (remaining[0] > 0 || remaining[1] > 0) {
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-          if (remaining[s] > 0 && __all_sync(FULL, tc::mbar_test_wait(&bars[1 + 2 * s], par[s]))) {
-            tc::fence_after_sync();
-            const uint32_t stm = tbase + (uint32_t)s * 256u;
-            const uint32_t lod = (WBYTES / 2u) >> 4;
-            auto issue = [&](uint32_t e) {
-              switch (stage[s]) {
-                case 0: geo_issue<NK, 0>(stm, wlo0, lod, two_term, e); break;
-                case 1: geo_issue<NK, 1>(stm, wlo0, lod, two_term, e); break;
-                case 2: geo_issue<NK, 2>(stm, wlo0, lod, two_term, e); break;
-                case 3: geo_issue<NK, 3>(stm, wlo0, lod, two_term, e); break;
-                case 4: geo_issue<NK, 4>(stm, wlo0, lod, two_term, e); break;
-                default: geo_issue<NK, 5>(stm, wlo0, lod, two_term, e); break;
-              }
-              tc::mma_commit2_el(&bars[2 + 2 * s], e);
-            };
-            if (issue_branch) {          // debug knob (KPN_ISSUE_BRANCH=1): only the elected lane enters the issue code
-              if (el) issue(1u);
-              __syncwarp();
-            } else {
-              issue(el);
-            }
-            par[s] ^= 1u;
-            stage[s] = stage[s] + 1 == GEO_NSTAGE ? 0 : stage[s] + 1;
-            --remaining[s];
-          }
-        }
-      }
-    }
-  } else {
+  {
     const int slot = warp >> 3, q4 = warp & 3, h = (warp >> 2) & 1;   // TMEM lane quarter = warp id % 4
     GeoCtx cx;
     cx.tm = tbase + (uint32_t)slot * 256u + ((uint32_t)(q4 * 32) << 16);
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl) : "r"(tc::smem_u32(&bars[1 + 2 * slot])), "r"(0u));
     cx.acc_ready = &bars[2 + 2 * slot];
     cx.ph = 0;
+    cx.issuer = (rank == 0 && q4 == 0 && h == 0) ? 1 : 0;
+    cx.a_ready = &bars[1 + 2 * slot];
+    cx.pha = 0;
+    cx.slot_tm = tbase + (uint32_t)slot * 256u;
+    cx.wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu;
+    cx.lod = (WBYTES / 2u) >> 4;
+    cx.el = tc::elect_one();
+    cx.lo_mask = two_term;
     cx.relaxed = relaxed_arrive;
     const int gb = 3 * (lane / 3);
     cx.l1 = (gb + (lane - gb + 1) % 3) & 31;
@@ -1009,7 +999,7 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
   tc::fence_before_sync();
   __syncthreads();
   tc::cluster_sync_all();     // the peer's TMEM / barriers must outlive the leader's last MMA and commit
-  if (warp == GEO_ROW_WARPS) tc::tmem_dealloc2(tbase, 512);
+  if (warp == 0) tc::tmem_dealloc2(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1123,12 +1113,11 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   const int max_clusters = num_sms / 2;
   int grid = 2 * (int)(pairs < 1 ? 1 : (pairs > max_clusters ? max_clusters : pairs));
   static const int relaxed_arrive = [] { const char* e = getenv("KPN_RELAXED_ARRIVE"); return e && e[0] == '0' ? 0 : 1; }();
-  static const int issue_branch = [] { const char* e = getenv("KPN_ISSUE_BRANCH"); return e && e[0] == '1' ? 1 : 0; }();
   // which stages get the W_lo pass (bits 0..5) and the A_lo pass (bits 6, 7 for stages 4, 5); KPN_LO_MASK overrides (experiments)
   static const int lo_env = [] { const char* e = getenv("KPN_LO_MASK"); return e ? (int)strtol(e, nullptr, 0) : -1; }();
   two_term = two_term ? (lo_env >= 0 ? lo_env : 0xFF) : 0xC0;
   shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, out5, lat, list2,
-                                                           count2, issue_branch, relaxed_arrive);
+                                                           count2, relaxed_arrive);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   long long g = (max_tiles + CSLOT - 1) / CSLOT;
