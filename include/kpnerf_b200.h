@@ -166,9 +166,10 @@ int kpn_query(kpn_ctx* ctx, const float* pts, const float* view, int n, float* o
  * kpn_get_stats when profiling is on).  Synchronises `stream` (debug/bench only). */
 int kpn_get_stats(kpn_ctx* ctx, kpn_stats* stats, void* stream);
 
-/* Debug: per-stage barrier-wait cycles of one row warp per CTA of the tensor-core kernel.  out16 (host, may be NULL)
- * receives [0..11] wait cycles at the 12 stages, [12] total tile cycles, [13] tiles recorded; then the counters are
- * reset (enable != 0) or freed (enable == 0).  Synchronises the device. */
+/* Debug: the device watchdog words of the tensor-core kernels.  Every barrier wait of those kernels gives up after ~2^20
+ * suspended polls instead of hanging the GPU; out16 (host, may be NULL) receives [0] flag (!= 0: some wait gave up; results of
+ * that launch are invalid), [1] block, [2] thread, [3] tag of the wait, [4] parity; [5..15] zero.  enable != 0 clears the
+ * flag afterwards.  kpn_get_stats reports a raised flag as KPN_ERR_CUDA.  Synchronises the device. */
 int kpn_debug_timing(kpn_ctx* ctx, int enable, unsigned long long* out16);
 
 /* enable != 0: bracket every shading-kernel launch with CUDA events on its stream (no sync). */
@@ -177,7 +178,9 @@ int kpn_set_profiling(kpn_ctx* ctx, int enable);
 /* Unit test hook for the tensor-core primitive (tests/test_gpu_umma.py): D(128,N) fp32 = A(128,K) fp16 * B(N,K)^T fp16
  * on one CTA through tcgen05.mma.  Device pointers.  variant bit0: B core-matrix arrangement, bit1: A from shared memory. */
 int kpn_selftest_umma(int N, int K, const void* A, const void* B, float* D, int variant, void* stream);
-/* Same for the CTA-pair form (cta_group::2): D(256,N) = A(256,K) * B(N,K)^T on a 2-CTA cluster. */
+/* Same for the CTA-pair form (cta_group::2): D(256,N) = A(256,K) * B(N,K)^T on a 2-CTA cluster, with the activation tile at
+ * tensor-memory column a_col and the accumulator at d_col (the geometry kernel's placements), issued by one thread (mode 0),
+ * warp-converged with an elected lane and predicated MMAs (mode 1, what the kernels use) or by the elected lane in a branch (2). */
 int kpn_selftest_umma2(int N, int K, const void* A, const void* B, float* D, int a_col, int d_col, int mode, void* stream);
 
 #ifdef __cplusplus

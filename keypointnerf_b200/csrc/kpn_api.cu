@@ -3,6 +3,7 @@
 // and kpn_tc.cu (tensor-core engine).
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -414,7 +415,14 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
     for (int i = 0; i < 7; ++i) dev[i] = user[i];
   }
 
-  long long Rc = (4ll << 20) / Smax;
+  // rays per chunk: bounded by the per-sample workspace (20 B/sample rgba + lists); fewer, larger launches amortise the
+  // persistent kernels' prologue (weight load) and tail.  KPN_CHUNK_SAMPLES overrides the default of 8 Mi samples.
+  static const long long chunk_samples = [] {
+    const char* e = getenv("KPN_CHUNK_SAMPLES");
+    long long v = e ? atoll(e) : 0;
+    return v >= (1ll << 16) && v <= (1ll << 28) ? v : (8ll << 20);
+  }();
+  long long Rc = chunk_samples / Smax;
   Rc = (Rc / 128) * 128;
   if (Rc < 128) Rc = 128;
   if (Rc > R) Rc = R;
@@ -542,19 +550,22 @@ extern "C" int kpn_get_stats(kpn_ctx* c, kpn_stats* stats, void* stream) {
   stats->shade_launches = c->ev_used / 2;
   stats->shade_ms = ms;
   c->ev_used = 0;
+  unsigned int wd[8];
+  KPN_CUDA(c, tc_watchdog_read(wd, false));
+  if (wd[0]) KPN_FAIL(c, KPN_ERR_CUDA, "device watchdog: a barrier wait gave up (block %u, thread %u, tag 0x%x, parity %u); results are invalid",
+                      wd[1], wd[2], wd[3], wd[4]);
   return KPN_OK;
 }
 
+// Debug hook.  out16[0..7] receive the device watchdog words of the tensor-core kernels (out16[0] != 0: a barrier wait gave
+// up at block out16[1], thread out16[2], tag out16[3]); enable != 0 clears them afterwards.
 extern "C" int kpn_debug_timing(kpn_ctx* c, int enable, unsigned long long* out16) {
   if (!c) return KPN_ERR_ARG;
   DeviceGuard g(c->device);
-  if (out16 && c->d_timing) {
-    KPN_CUDA(c, cudaDeviceSynchronize());
-    KPN_CUDA(c, cudaMemcpy(out16, c->d_timing, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  }
-  if (enable && !c->d_timing) KPN_CUDA(c, cudaMalloc(&c->d_timing, 16 * sizeof(unsigned long long)));
-  if (enable) KPN_CUDA(c, cudaMemset(c->d_timing, 0, 16 * sizeof(unsigned long long)));
-  if (!enable && c->d_timing) { cudaFree(c->d_timing); c->d_timing = nullptr; }
+  KPN_CUDA(c, cudaDeviceSynchronize());
+  unsigned int wd[8];
+  KPN_CUDA(c, tc_watchdog_read(wd, enable != 0));
+  if (out16) { for (int i = 0; i < 16; ++i) out16[i] = i < 8 ? wd[i] : 0ull; }
   return KPN_OK;
 }
 

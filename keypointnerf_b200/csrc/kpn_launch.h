@@ -26,6 +26,7 @@ cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t
                             void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st,
                             unsigned long long* timing = nullptr);
 size_t tc_pair_blob_bytes(int n_kpt);
+cudaError_t tc_watchdog_read(unsigned int out[8], bool reset);
 size_t tc_weight_blob_bytes(int n_kpt);
 size_t tc_weight_lo_bytes(int n_kpt);
 bool tc_supported(int n_views, int n_kpt, int sp_level);

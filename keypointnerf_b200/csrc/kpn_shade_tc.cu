@@ -117,7 +117,7 @@ __device__ __forceinline__ void signal_a(RowCtx& c) {
     asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(c.a_ready)) : "memory");
 }
 __device__ __forceinline__ void wait_acc(RowCtx& c) {
-  tc::mbar_wait(c.acc_ready, c.ph);
+  tc::mbar_wait(c.acc_ready, c.ph, 0x20u);
   c.ph ^= 1u;
   tc::fence_after_sync();
 }
@@ -211,7 +211,7 @@ __device__ __forceinline__ void geo_signal(const GeoCtx& c, int lane) {
   }
 }
 __device__ __forceinline__ void geo_wait(GeoCtx& c) {
-  tc::mbar_wait(c.acc_ready, c.ph);
+  tc::mbar_wait(c.acc_ready, c.ph, 0x100u);
   c.ph ^= 1u;
   tc::fence_after_sync();
 }
@@ -221,7 +221,7 @@ __device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint3
 template <int NK, int STAGE>
 __device__ __forceinline__ void geo_mma(GeoCtx& c) {
   if (c.issuer) {
-    tc::mbar_wait(c.a_ready, c.pha);
+    tc::mbar_wait(c.a_ready, c.pha, 0x10u + (uint32_t)STAGE);
     c.pha ^= 1u;
     tc::fence_after_sync();
     geo_issue<NK, STAGE>(c.slot_tm, c.wlo0, c.lod, c.lo_mask, c.el);
@@ -457,7 +457,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     if (h == 1 && w == 4) return;
     const bool f8w = (h == 1) && (w == 3);
     const MapDesc& m = f8w ? sc.f8 : sc.f64;
-    const Taps t = make_taps(nu, nv, m.W, m.H);
+    const Taps t = make_taps(nu, nv, m.W, m.H);   // recomputed per window: holding the taps across the tile costs more (registers)
     pwt[0] = t.w00; pwt[1] = t.w01; pwt[2] = t.w10; pwt[3] = t.w11;
     taps_issue<2>(m, v, t, f8w ? 0 : (h == 0 ? 2 * w : FG + 2 * w), pr);
   };
@@ -909,7 +909,7 @@ __device__ __forceinline__ void load_weights(uint8_t* dst, const uint8_t* src, u
     uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
     tc::bulk_g2s(dst + off, src + off, n, wbar);
   }
-  tc::mbar_wait(wbar, 0);
+  tc::mbar_wait(wbar, 0, 0x30u);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1045,10 +1045,13 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
       int remaining[CSLOT], stage[CSLOT], left = 0;
       uint32_t par[CSLOT];
       for (int s = 0; s < CSLOT; ++s) { remaining[s] = tiles_of_slot(s) * COL_NSTAGE; stage[s] = 0; par[s] = 0; left += remaining[s]; }
+      uint32_t idle = 0;
       while (left > 0) {
+        if ((++idle & 1023u) == 0u && tc::wd_give_up(idle, 1u << 24, 0x40u, 0u)) break;
 #pragma unroll
         for (int s = 0; s < CSLOT; ++s) {
           if (remaining[s] > 0 && __all_sync(FULL, tc::mbar_test_wait(&bars[1 + 2 * s], par[s]))) {
+            idle = 0;
             tc::fence_after_sync();
             const uint32_t stm = tbase + (uint32_t)s * 128u;
             switch (stage[s]) {
@@ -1134,6 +1137,16 @@ cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t
                               (int2*)list2, count2, num_sms, st, timing);
   return launch_tc_impl<24>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
                             (int2*)list2, count2, num_sms, st, timing);
+}
+
+// Watchdog state of this module's kernels: out[0] != 0 -> some barrier wait gave up at block out[1], thread out[2], tag out[3].
+cudaError_t tc_watchdog_read(unsigned int out[8], bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, tc::kpn_wd, 8 * sizeof(unsigned int));
+  if (e == cudaSuccess && reset) {
+    const unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e = cudaMemcpyToSymbol(tc::kpn_wd, z, sizeof(z));
+  }
+  return e;
 }
 
 size_t tc_pair_blob_bytes(int n_kpt) { return 2 * (size_t)make_tc_plan(n_kpt).st[GEO_NSTAGE].off; }

@@ -43,8 +43,23 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Watchdog.  A barrier wait that has not completed after ~2^20 suspended polls is a protocol bug; instead of hanging the GPU
+// the waiter records where it gave up, raises this module's abort flag (every other wait then gives up within 256 polls) and
+// returns, so that the kernel terminates (with garbage results) and the host can report the location (tc_watchdog_read).
+static __device__ unsigned int kpn_wd[8];   // [0] flag, [1] block, [2] thread, [3] tag, [4] parity
+__device__ __forceinline__ bool wd_give_up(uint32_t spins, uint32_t limit, uint32_t tag, uint32_t parity) {
+  const bool aborted = *reinterpret_cast<volatile unsigned int*>(&kpn_wd[0]) != 0u;
+  if (!aborted && spins <= limit) return false;
+  if (!aborted && atomicCAS(&kpn_wd[0], 0u, 1u) == 0u) {
+    kpn_wd[1] = blockIdx.x; kpn_wd[2] = threadIdx.x; kpn_wd[3] = tag; kpn_wd[4] = parity;
+    __threadfence();
+  }
+  return true;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0u && wd_give_up(spins, 1u << 20, tag, parity)) return;
   }
 }
 

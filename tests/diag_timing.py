@@ -1,22 +1,33 @@
-"""Diagnostic (not a pytest): per-stage wait vs compute cycles of the tensor-core row warps."""
+"""Diagnostic (not a pytest): run the tiny golden query + one small render on the tensor-core engine and print the device
+watchdog words (kpn_debug_timing): [flag, block, thread, tag, parity].  A non-zero flag means a barrier wait gave up."""
 import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from keypointnerf_b200 import synthetic as syn
 from keypointnerf_b200.testing import build_model, scene_tensors
-scene = syn.make_scene(src_size=512, n_kpt=18); net = build_model(syn.make_weights(18), 18, "cuda:0")
-target = syn.make_target(size=512); a = scene_tensors(scene, target, "cuda:0")
-m = net._bind_scene(a["cam"], a["feat_geo"], a["feat_tex"], a["sp_data"], a["img"], a["fg"], a["bounds"])
-names = ["L0", "L1", "L2", "L3", "P0|CMP", "P1", "BASE0", "BASE1", "VIS1A", "VIS1B", "VIS2A", "OUT0"]
-for eng in (2, 0):
-    kw = dict(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=2, nx=256, ny=256, S_c=128, engine=eng)
-    m.render(**kw); torch.cuda.synchronize()
-    m.lib.kpn_debug_timing(m.ctx, 1, None)
-    m.render(**kw); torch.cuda.synchronize()
+from tests.util import load_golden, scene_from_meta
+
+
+def watchdog(m, tag):
     out = (C.c_ulonglong * 16)()
-    m.lib.kpn_debug_timing(m.ctx, 0, out)
-    o = np.array(list(out), dtype=np.float64)
-    tiles = max(o[13], 1)
-    print(f"engine {eng}: tiles recorded {int(o[13])}, cycles/tile {o[12]/tiles:.0f}, total wait/tile {o[:12].sum()/tiles:.0f} ({100*o[:12].sum()/o[12]:.1f}%)")
-    print(f"   colour kernel: tiles {int(o[15])}, cycles/tile {o[14]/max(o[15],1):.0f}")
-    print("   wait cycles per stage:", ", ".join(f"{n}={o[i]/tiles:.0f}" for i, n in enumerate(names)))
+    m.lib.kpn_debug_timing(m.ctx, 1, out)
+    w = list(out)[:5]
+    print(f"{tag}: watchdog flag={w[0]} block={w[1]} thread={w[2]} (warp {w[2] // 32}) tag=0x{w[3]:x} parity={w[4]}")
+
+
+for name in sys.argv[1:] or ["tiny"]:
+    g, meta, sha = load_golden(name)
+    scene, weights, target = scene_from_meta(meta)
+    net = build_model(weights, meta["n_kpt"], "cuda:0")
+    a = scene_tensors(scene, target, "cuda:0")
+    net.engine = 0
+    pts = torch.from_numpy(g["query_pts"]).cuda()[None]
+    view = torch.from_numpy(g["query_view"]).cuda()[None]
+    with torch.no_grad():
+        out, valid = net.query(pts, a["cam"], a["feat_geo"], a["feat_tex"], n_views=3, sp_data=a["sp_data"], tx_data={"img": a["img"]},
+                               view=view, src_foreground_mask=a["fg"], bounds=a["bounds"])
+    torch.cuda.synchronize()
+    v = g["query_valid"]
+    o = out[0].cpu().numpy()
+    print(name, "n", len(v), "valid", int(v.sum()), "rgb err", float(np.abs(o[v][:, 2:] - g["query_out"][v][:, 2:]).max()),
+          "rad err", float(np.abs(o[v][:, 1] - g["query_out"][v][:, 1]).max()))
+    watchdog(net.marcher(), name)
