@@ -167,7 +167,9 @@ __global__ void compact_kernel(const DevScene* __restrict__ sc, SampleSrc src, l
                                int* __restrict__ list, int* __restrict__ counter, float* __restrict__ out5,
                                uint8_t* __restrict__ valid_out) {
   const DevScene& S = *sc;
-  for (long long base = (blockIdx.x * (long long)blockDim.x) ; base < n; base += (long long)gridDim.x * blockDim.x) {
+  __shared__ int s_cnt[8];
+  __shared__ int s_base;
+  for (long long base = (blockIdx.x * (long long)blockDim.x) ; base < n; base += (long long)gridDim.x * blockDim.x) {   // block-uniform trip count
     long long i = base + threadIdx.x;
     bool ok = false;
     if (i < n) {
@@ -183,15 +185,20 @@ __global__ void compact_kernel(const DevScene* __restrict__ sc, SampleSrc src, l
       }
       if (valid_out) valid_out[i] = ok ? 1 : 0;
     }
-    unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (m) {
-      int lane = threadIdx.x & 31;
-      int leader = __ffs(m) - 1;
-      int pos = 0;
-      if (lane == leader) pos = atomicAdd(counter, __popc(m));
-      pos = __shfl_sync(0xffffffffu, pos, leader);
-      if (ok) list[pos + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    // block-aggregated append: one atomic per 256 samples instead of one per warp (the single counter serialises in L2)
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[wid] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(counter, tot) : 0;
     }
+    __syncthreads();
+    if (ok) list[s_base + s_cnt[wid] + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    __syncthreads();   // s_cnt / s_base are rewritten by the next iteration
   }
 }
 
@@ -534,28 +541,56 @@ shade_simt_kernel(const DevScene* __restrict__ scp, const DevWeightsF32* __restr
 // compositing (reference src/model.py:1150-1176)
 // ------------------------------------------------------------------------------------------------
 // rgba (nr,S,5) = [alpha, sdf, r, g, b]; z (nr,S).  Planar outputs indexed by global ray r0+i.
-__global__ void composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, int r0, int nr, int S,
-                                 long long plane, float* __restrict__ color, float* __restrict__ depth,
-                                 float* __restrict__ alpha, float* __restrict__ sdf, float* __restrict__ contrib) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nr) return;
-  const float* q = rgba + (long long)i * S * 5;
-  const float* zz = z + (long long)i * S;
-  float T = 1.0f, acc = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f, cs = 0.0f;
-  for (int k = 0; k < S; ++k) {
-    float dist = k + 1 < S ? zz[k + 1] - zz[k] : 1e10f;
-    float a = 1.0f - expf(-q[5 * k] * dist);
-    float c = a * T;
-    T *= (1.0f - a);
-    acc += c; cr += c * q[5 * k + 2]; cg += c * q[5 * k + 3]; cb += c * q[5 * k + 4];
-    cd += c * zz[k]; cs += c * q[5 * k + 1];
-    if (contrib) contrib[(long long)i * S + k] = c;
+// One WARP per ray: lane l takes samples l, l+32, ... (coalesced reads), the transmittance T_k = prod_{j<k} (1 - a_j) is an
+// exclusive product scan across the lanes carried from one group of 32 samples to the next, the ray sums are warp reductions.
+__global__ void __launch_bounds__(128)
+composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, int r0, int nr, int S,
+                 long long plane, float* __restrict__ color, float* __restrict__ depth,
+                 float* __restrict__ alpha, float* __restrict__ sdf, float* __restrict__ contrib) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nr; i += gridDim.x * wpb) {
+    const float* q = rgba + (long long)i * S * 5;
+    const float* zz = z + (long long)i * S;
+    float Tc = 1.0f;   // transmittance in front of this group of 32 samples
+    float acc = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f, cs = 0.0f;
+    for (int k0 = 0; k0 < S; k0 += 32) {
+      const int k = k0 + lane;
+      float a = 0.0f, zk = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f, q4 = 0.0f;
+      if (k < S) {
+        zk = zz[k];
+        const float dist = k + 1 < S ? zz[k + 1] - zk : 1e10f;
+        a = 1.0f - expf(-q[5 * k] * dist);
+        q1 = q[5 * k + 1]; q2 = q[5 * k + 2]; q3 = q[5 * k + 3]; q4 = q[5 * k + 4];
+      }
+      float p = 1.0f - a;   // inclusive product scan of (1 - a)
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, p, d);
+        if (lane >= d) p *= t;
+      }
+      float ex = __shfl_up_sync(0xffffffffu, p, 1);
+      if (lane == 0) ex = 1.0f;
+      const float c = a * (Tc * ex);
+      Tc *= __shfl_sync(0xffffffffu, p, 31);
+      if (k < S) {
+        acc += c; cr += c * q2; cg += c * q3; cb += c * q4; cd += c * zk; cs += c * q1;
+        if (contrib) contrib[(long long)i * S + k] = c;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, d); cr += __shfl_xor_sync(0xffffffffu, cr, d); cg += __shfl_xor_sync(0xffffffffu, cg, d);
+      cb += __shfl_xor_sync(0xffffffffu, cb, d); cd += __shfl_xor_sync(0xffffffffu, cd, d); cs += __shfl_xor_sync(0xffffffffu, cs, d);
+    }
+    if (lane == 0) {
+      const long long r = r0 + i;
+      if (color) { color[r] = cr; color[plane + r] = cg; color[2 * plane + r] = cb; }
+      if (alpha) alpha[r] = acc;
+      if (depth) depth[r] = cd / (acc + 1e-8f);
+      if (sdf) sdf[r] = cs / (acc + 1e-8f);
+    }
   }
-  long long r = r0 + i;
-  if (color) { color[r] = cr; color[plane + r] = cg; color[2 * plane + r] = cb; }
-  if (alpha) alpha[r] = acc;
-  if (depth) depth[r] = cd / (acc + 1e-8f);
-  if (sdf) sdf[r] = cs / (acc + 1e-8f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -651,7 +686,7 @@ cudaError_t launch_shade_simt(const DevScene* sc, const DevWeightsF32* W, const 
 }
 cudaError_t launch_composite(const float* rgba, const float* z, int r0, int nr, int S, long long plane, float* color,
                              float* depth, float* alpha, float* sdf, float* contrib, cudaStream_t st) {
-  composite_kernel<<<grid_for(nr, 128, 1 << 30), 128, 0, st>>>(rgba, z, r0, nr, S, plane, color, depth, alpha, sdf, contrib);
+  composite_kernel<<<grid_for((long long)nr * 32, 128, 148 * 64), 128, 0, st>>>(rgba, z, r0, nr, S, plane, color, depth, alpha, sdf, contrib);
   return cudaGetLastError();
 }
 cudaError_t launch_importance(const float* contrib, const float* z, int nr, int Sc, int Sf, float* zout, cudaStream_t st) {

@@ -251,6 +251,8 @@ __device__ __forceinline__ uint32_t sp_pair(uint32_t a0, uint32_t a1) {
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
+__device__ __forceinline__ uint32_t sel3(int v, uint32_t a, uint32_t b, uint32_t c) { return v == 0 ? a : (v == 1 ? b : c); }
+
 // store N registers to consecutive tensor-memory columns starting at column C0 (relative alignment known at compile time)
 template <int N, int C0>
 __device__ __forceinline__ void st_cols(uint32_t addr, const uint32_t* r) {
@@ -576,9 +578,22 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
       const float l0 = u2f(h ? rc[4 + 2 * i] : rc[2 * i]), l1 = u2f(h ? rc[5 + 2 * i] : rc[2 * i + 1]);
       latp[i] = tc::pack_h2(l0, l1);
     }
-    uint32_t hi[16], lo[16];
+    // The three view rows of a sample hold the same pooled input, hence (to fp32 rounding) the same accumulator row: lane v
+    // activates only the column pairs j = 3k + v of its own row and the group all-gathers the packed results by shuffle.
+    uint32_t hk[6], lk[6];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) split_h2(sp_fast(u2f(r[2 * i])), sp_fast(u2f(r[2 * i + 1])), hi[i], lo[i]);
+    for (int k = 0; k < 6; ++k) {   // k = 5: only pair 15 exists; lanes with v > 0 recompute it, nobody reads their copy
+      const int j0 = 3 * k, j1 = min(3 * k + 1, 15), j2 = min(3 * k + 2, 15);
+      const float x0 = u2f(sel3(v, r[2 * j0], r[2 * j1], r[2 * j2])), x1 = u2f(sel3(v, r[2 * j0 + 1], r[2 * j1 + 1], r[2 * j2 + 1]));
+      split_h2(sp_fast(x0), sp_fast(x1), hk[k], lk[k]);
+    }
+    uint32_t hi[16], lo[16];
+    const int gb = lane - v;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      hi[j] = __shfl_sync(FULL, hk[j / 3], gb + j % 3);
+      lo[j] = __shfl_sync(FULL, lk[j / 3], gb + j % 3);
+    }
     tc::tmem_st16(A + 16u * (uint32_t)h, hi);
     tc::tmem_st16(A + 32u + 16u * (uint32_t)h, lo);
     if (h == 0) {
@@ -597,15 +612,19 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     uint32_t r[32];
     tc::tmem_ld32(A + 128u + 32u * (uint32_t)h, r);
     tc::wait_ld();
-    const float4* w0 = reinterpret_cast<const float4*>(wp2 + 32 * h);
-    const float4* w1 = reinterpret_cast<const float4*>(wp2 + 64 + 32 * h);
+    // same split over the three lanes of the group: lane v takes columns 3k + v of its 32, the partial dots are group sums
+    const float* w0 = wp2 + 32 * h + v;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 a0 = w0[i], a1 = w1[i];
-      const float h0 = sp_fast(u2f(r[4 * i])), h1 = sp_fast(u2f(r[4 * i + 1])), h2 = sp_fast(u2f(r[4 * i + 2])), h3 = sp_fast(u2f(r[4 * i + 3]));
-      g0 = fmaf(a0.x, h0, g0); g0 = fmaf(a0.y, h1, g0); g0 = fmaf(a0.z, h2, g0); g0 = fmaf(a0.w, h3, g0);
-      rad = fmaf(a1.x, h0, rad); rad = fmaf(a1.y, h1, rad); rad = fmaf(a1.z, h2, rad); rad = fmaf(a1.w, h3, rad);
+    for (int k = 0; k < 11; ++k) {
+      const int c0 = 3 * k, c1 = min(3 * k + 1, 31), c2 = min(3 * k + 2, 31);
+      const float hh = sp_fast(u2f(sel3(v, r[c0], r[c1], r[c2])));
+      const bool live = 3 * k + v < 32;   // k = 10: columns 30 and 31 exist, 32 does not
+      const float a0 = live ? w0[3 * k] : 0.0f, a1 = live ? w0[64 + 3 * k] : 0.0f;
+      g0 = fmaf(a0, hh, g0);
+      rad = fmaf(a1, hh, rad);
     }
+    g0 = gsum(cx, g0);
+    rad = gsum(cx, rad);
   }
   // ---- the h = 1 thread hands its partial sums and latent half to its partner (same row, other warp) through shared memory
   GeoXch* xr = xch + (32 * q4 + lane);
