@@ -209,7 +209,7 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
     const size_t geo_bytes = tc_weight_lo_bytes(w->n_kpt);          // bytes of the full W_hi tiles of stages 0..5
     std::vector<__half> pair(tc_pair_blob_bytes(w->n_kpt) / 2, __float2half_rn(0.0f));   // [rank][hi halves | lo halves]
     // stage -> (layer, first row in the tile); stage 4 stacks the density layer 0 and the colour compress layer
-    const int stage_layer[TC_NSTAGE] = {L_GEO0, L_GEO1, L_GEO2, L_GEO3, L_DEN0, L_DEN1, L_BASE0, L_BASE1, L_VIS1A, L_VIS1B, L_VIS2A, L_OUT0};
+    const int stage_layer[TC_NSTAGE] = {L_GEO0, L_GEO1, L_GEO2, L_GEO3, L_DEN0, L_DEN1, L_BASE0, L_BASE1, L_VIS1A, L_VIS1B, L_VIS2A, L_OUT0, L_RE1};
     auto put_one = [&](int stage, int n, int kk, float wv) {
       const int Np = plan.st[stage].Np;
       const size_t at = (plan.st[stage].off + tc::core_offset_bytes(n, kk, Np)) / 2;
@@ -227,7 +227,7 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
       for (int o = 0; o < L.n_out; ++o) {
         for (int i = 0; i < L.n_in; ++i)
           put_one(stage, row0 + o, stage < 6 ? tc_kmap(stage, w->n_kpt, i) : i, We[layer][(size_t)o * L.n_in + i]);
-        if (stage < 6) put_one(stage, row0 + o, tc_kbias(stage, w->n_kpt), L.bias[o]);   // bias row (activation column == 1)
+        if (stage < 6 || stage == 12) put_one(stage, row0 + o, tc_kbias(stage, w->n_kpt), L.bias[o]);   // bias row (activation column == 1)
       }
     };
     for (int sidx = 0; sidx < TC_NSTAGE; ++sidx) put(sidx, stage_layer[sidx], 0);

@@ -36,7 +36,7 @@ constexpr int ROW_WARPS = 4;
 constexpr int NSLOT = 2;                                  // geo kernel tile slots
 constexpr int CSLOT = 3;                                  // colour kernel tile slots
 constexpr int TCC_THREADS = (CSLOT * ROW_WARPS + 1) * 32; // 416: 12 row warps + issuer
-constexpr int GEO_NSTAGE = 6, COL_NSTAGE = 6;
+constexpr int GEO_NSTAGE = 6, COL_NSTAGE = 7;   // colour: RE1 (stage 12) then stages 6..11
 constexpr int SPW = 10;                                   // samples per warp (3 views each)
 constexpr int SPT = SPW * ROW_WARPS;                      // samples per tile
 constexpr float LOG2E = 1.4426950408889634f;
@@ -713,22 +713,30 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
       rd[3] = r[0] * d[0] + r[1] * d[1] + r[2] * d[2];
     }
   }
-  {  // ray-direction encoder 4->16->35, ELU, added onto the features (src/model.py:1279-1284); fp32
-    float h16[16];
+  {  // ray-direction encoder 4->16->35, ELU, added onto the features (src/model.py:1279-1284): first layer in fp32 on the CUDA
+     // cores, second layer (stage 12, bias as K row 16) on the tensor core
+    uint32_t a[16];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) {
-      float acc = C.b_re0[o];
+    for (int o = 0; o < 16; o += 2) {
+      float acc0 = C.b_re0[o], acc1 = C.b_re0[o + 1];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc = fmaf(C.w_re0[o][i], rd[i], acc);
-      h16[o] = elu_fast(acc);
+      for (int i = 0; i < 4; ++i) { acc0 = fmaf(C.w_re0[o][i], rd[i], acc0); acc1 = fmaf(C.w_re0[o + 1][i], rd[i], acc1); }
+      a[o / 2] = tc::pack_h2(elu_fast(acc0), elu_fast(acc1));
     }
+    a[8] = 0x00003C00u;   // (1, 0): bias column
 #pragma unroll
-    for (int o = 0; o < 35; ++o) {
-      float acc = C.b_re1[o];
+    for (int i = 9; i < 16; ++i) a[i] = 0u;
+    tc::tmem_st16(R0, a);
+    signal_a(cx);
+    wait_acc(cx);
+    uint32_t r[32], r2[8];
+    tc::tmem_ld32(R1, r);
+    tc::tmem_ld8(R1 + 32, r2);
+    tc::wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc = fmaf(C.w_re1[o][i], h16[i], acc);
-      f[o] += elu_fast(acc);
-    }
+    for (int o = 0; o < 32; ++o) f[o] += elu_fast(u2f(r[o]));
+#pragma unroll
+    for (int o = 32; o < 35; ++o) f[o] += elu_fast(u2f(r2[o - 32]));
   }
   float om;  // blending weight (src/model.py:1286-1289), mask == 1
   {
@@ -1074,11 +1082,12 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
             tc::fence_after_sync();
             const uint32_t stm = tbase + (uint32_t)s * 128u;
             switch (stage[s]) {
-              case 0: col_issue<NK, 6>(stm, wlo0, el); break;
-              case 1: col_issue<NK, 7>(stm, wlo0, el); break;
-              case 2: col_issue<NK, 8>(stm, wlo0, el); break;
-              case 3: col_issue<NK, 9>(stm, wlo0, el); break;
-              case 4: col_issue<NK, 10>(stm, wlo0, el); break;
+              case 0: col_issue<NK, 12>(stm, wlo0, el); break;
+              case 1: col_issue<NK, 6>(stm, wlo0, el); break;
+              case 2: col_issue<NK, 7>(stm, wlo0, el); break;
+              case 3: col_issue<NK, 8>(stm, wlo0, el); break;
+              case 4: col_issue<NK, 9>(stm, wlo0, el); break;
+              case 5: col_issue<NK, 10>(stm, wlo0, el); break;
               default: col_issue<NK, 11>(stm, wlo0, el); break;
             }
             tc::mma_commit_el(&bars[2 + 2 * s], el);

@@ -6,10 +6,11 @@
 
 namespace kpn {
 
-constexpr int TC_NSTAGE = 12;
-// stage:            0 L0   1 L1  2 L2  3 L3  4 P0|CMP 5 P1 6 BASE0 7 BASE1 8 VIS1A 9 VIS1B 10 VIS2A 11 OUT0
-// Np (padded N):    128    128   128   64    96       64   64      32      32      48      32       16
-// Kp (padded K):    K0P    144   144   128   144      80   112     64      32      32      32       48
+constexpr int TC_NSTAGE = 13;
+// stage:            0 L0   1 L1  2 L2  3 L3  4 P0|CMP 5 P1 6 BASE0 7 BASE1 8 VIS1A 9 VIS1B 10 VIS2A 11 OUT0 12 RE1
+// Np (padded N):    128    128   128   64    96       64   64      32      32      48      32       16      48
+// Kp (padded K):    K0P    144   144   128   144      80   112     64      32      32      32       48      32
+// Stage 12 (second ray-encoder layer 16->35 of the colour head, executed FIRST in the colour kernel) also carries its bias row.
 // The geometry stages (0..5) carry their bias as one extra K row (the activation tile holds a constant 1 there), so their
 // epilogues have no per-column constants.  Stage 0 additionally permutes its inputs (tc_kmap) so that the two threads
 // that build a row's input each write one contiguous, naturally aligned run of tensor-memory columns.
@@ -45,7 +46,7 @@ __host__ __device__ constexpr int tc_kmap(int stage, int n_kpt, int i) {
   const int c = i - 7 * n_kpt;
   return c < FA ? 2 * 7 * PA + c : 2 * (7 * PA + FA / 2 + 7 * (NP - PA)) + (c - FA);
 }
-// K index of the bias row of a geometry stage
+// K index of the bias row of a geometry stage (or of stage 12)
 __host__ __device__ constexpr int tc_kbias(int stage, int n_kpt) {
   switch (stage) {
     case 0: return 2 * (7 * (n_kpt / 2) + 32);
@@ -53,14 +54,15 @@ __host__ __device__ constexpr int tc_kbias(int stage, int n_kpt) {
     case 2: return 136;
     case 3: return 120;
     case 4: return 128;
+    case 12: return 16;
     default: return 64;
   }
 }
 
 __host__ __device__ constexpr TcPlan make_tc_plan(int n_kpt) {
   TcPlan p{};
-  const int Kp[TC_NSTAGE] = {tc_k0p(n_kpt), 144, 144, 128, 144, 80, 112, 64, 32, 32, 32, 48};
-  const int Np[TC_NSTAGE] = {128, 128, 128, 64, 96, 64, 64, 32, 32, 48, 32, 16};
+  const int Kp[TC_NSTAGE] = {tc_k0p(n_kpt), 144, 144, 128, 144, 80, 112, 64, 32, 32, 32, 48, 32};
+  const int Np[TC_NSTAGE] = {128, 128, 128, 64, 96, 64, 64, 32, 32, 48, 32, 16, 48};
   uint32_t off = 0;
   for (int i = 0; i < TC_NSTAGE; ++i) {
     p.st[i].Kp = Kp[i];
