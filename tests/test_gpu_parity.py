@@ -356,3 +356,30 @@ def test_full_frame_properties_at_baseline_size():
     print(f"512^2x128 frame, tcgen05 vs fp32 engine: max rgb err {e_rob:.2e} on {1 - frac_flipped:.4f} of rays, psnr {p:.1f} dB; "
           f"final-sample step flips on {frac_flipped:.4%} of rays")
     assert e_rob < 1e-3 and p > 60.0 and frac_flipped < 0.01
+
+
+def test_24_keypoint_frame_many_tiles_per_slot():
+    """24 keypoints (configs/zju.json's n_kpt) take the tensor-core path WITHOUT the next-tile staging buffer (shared-memory
+    budget); a 192x192x96 frame gives every tile slot several tiles, i.e. the persistent loop, the ghost tiles and the
+    inline gathers of that path.  Checked against the fp32 engine like the baseline-size frame, and the device watchdog
+    (kpn_debug_timing) must report that no barrier wait gave up."""
+    import ctypes as C
+    scene = syn.make_scene(src_size=256, n_kpt=24)
+    weights = syn.make_weights(24)
+    target = syn.make_target(size=192)
+    net = build_model(weights, 24, "cuda:0")
+    a = scene_tensors(scene, target, "cuda:0")
+    m = net._bind_scene(a["cam"], a["feat_geo"], a["feat_tex"], a["sp_data"], a["img"], a["fg"], a["bounds"])
+    kw = dict(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, S_c=96, x0=0, y0=0, step=1, nx=192, ny=192)
+    frame = m.render(engine=0, **kw)
+    st = m.stats()
+    assert st["samples_valid"] > 148 * 2 * 40 * 4, "scene too empty to give every slot several tiles"
+    ref = m.render(engine=1, **kw)
+    torch.cuda.synchronize()
+    wd = (C.c_ulonglong * 16)()
+    assert m.lib.kpn_debug_timing(m.ctx, 1, wd) == 0 and wd[0] == 0, f"device watchdog fired: {list(wd)[:5]}"
+    flipped = (frame["alpha"] - ref["alpha"]).abs() > 0.05
+    err = (frame["tex_fg"] - ref["tex_fg"]).abs().amax(0)
+    e_rob = float(err[~flipped].max())
+    print(f"24-keypoint 192^2x96 frame, tcgen05 vs fp32 engine: max rgb err {e_rob:.2e}, flipped {float(flipped.float().mean()):.4%}")
+    assert e_rob < 1e-3 and float(flipped.float().mean()) < 0.01
