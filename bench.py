@@ -285,7 +285,7 @@ def main():
     traffic, traffic_src = ncu_traffic()
     roofline = {"bound": "tensor", "kernel": "shade_geo_kernel + shade_color_kernel (per-sample gather+encode+MLPs; geometry is ~85% of it)",
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": (ach / pk["tflops"]) if ach else None,
-                "traffic": traffic, "traffic_unit": "DRAM bytes per launch pair (one chunk of 8 Mi samples), ncu --set full",
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch pair (one chunk = one 512x512x128 frame), ncu --set full",
                 "traffic_source": traffic_src,
                 "peak_source": pk["source"], "flop_per_sample": fps, "valid_samples_per_step": valid_per_step,
                 "valid_frac": valid_per_step / float(SIZE * SIZE * S_C), "shade_ms_per_step": shade_ms / args.steps,

@@ -60,7 +60,7 @@ def ncu_kernel(name, kern_sub, fn_name):
     hdr, units, val = rows[0], rows[1], rows[2]
     traffic = {}
     with open(os.path.join(P, f"{outp}_ncu_{name}_metrics.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none, one launch of shade_{name}_kernel<18> inside bench.py (512x512x128 frame, one chunk of 65536 rays)\n")
+        f.write(f"# ncu --set full --clock-control none, one launch of shade_{name}_kernel<18> inside bench.py (one chunk = the whole 512x512x128 frame)\n")
         for h, u, v in zip(hdr, units, val):
             if any(k in h for k in KEEP) and ".max" not in h and ".min" not in h and ".sum.pct" not in h:
                 f.write(f"{h:95s} {v:>20s} {u}\n")
@@ -87,6 +87,6 @@ def ncu_kernel(name, kern_sub, fn_name):
 
 launches()
 tr = {"geo": ncu_kernel("geo", "shade_geo_kernelILi18", "geo_tile"), "color": ncu_kernel("color", "shade_color_kernelILi18", "color_tile")}
-json.dump({"source": f"ncu --set full capture gpurun_out/{tag}_*.ncu-rep (one launch each, one chunk of 8 Mi samples = 65536 rays x 128 samples)", "kernels": tr},
+json.dump({"source": f"ncu --set full capture gpurun_out/{tag}_*.ncu-rep (one launch each; a launch covers one chunk = the whole 512x512x128 frame at the default chunk size)", "kernels": tr},
           open(os.path.join(P, f"{outp}_traffic.json"), "w"), indent=1)
 print(json.dumps(tr, indent=1))
