@@ -43,8 +43,8 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Watchdog.  A barrier wait that has not completed after ~2^20 suspended polls is a protocol bug; instead of hanging the GPU
-// the waiter records where it gave up, raises this module's abort flag (every other wait then gives up within 256 polls) and
+// Watchdog.  A barrier wait that has not completed after ~2^16 suspended polls (of up to 20 us each) is a protocol bug; instead of hanging the GPU
+// the waiter records where it gave up, raises this module's abort flag (every other wait then gives up within 16 polls) and
 // returns, so that the kernel terminates (with garbage results) and the host can report the location (tc_watchdog_read).
 static __device__ unsigned int kpn_wd[8];   // [0] flag, [1] block, [2] thread, [3] tag, [4] parity
 __device__ __forceinline__ bool wd_give_up(uint32_t spins, uint32_t limit, uint32_t tag, uint32_t parity) {
@@ -56,10 +56,21 @@ __device__ __forceinline__ bool wd_give_up(uint32_t spins, uint32_t limit, uint3
   }
   return true;
 }
+// try_wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint elapses, instead of
+// re-polling every few hundred cycles (a third of the row warps wait at any time; their polls compete for issue slots).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0u && wd_give_up(spins, 1u << 20, tag, parity)) return;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if ((++spins & 15u) == 0u && wd_give_up(spins, 1u << 16, tag, parity)) return;
   }
 }
 
