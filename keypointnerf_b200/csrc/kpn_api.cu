@@ -70,7 +70,7 @@ struct kpn_ctx {
   DevBuf stage[4];             // host-sourced maps before packing
   DevBuf atlas[4];             // f64, f8, ftex, img (channel-last fp32)
   DevBuf atlas_fg;
-  DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in, ws_lat, ws_list2;
+  DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in, ws_lat, ws_list2, ws_ert;
   unsigned long long launches = 0;
   bool profiling = false;
   unsigned long long* d_timing = nullptr;   // [16] debug: per-stage wait cycles of the tensor-core row warps
@@ -133,7 +133,7 @@ extern "C" void kpn_destroy(kpn_ctx* c) {
   c->atlas_fg.release();
   c->ws_z.release(); c->ws_rgba.release(); c->ws_list.release(); c->ws_rayd.release(); c->ws_raynf.release();
   c->ws_contrib.release(); c->ws_zfine.release(); c->ws_out.release(); c->ws_in.release();
-  c->ws_lat.release(); c->ws_list2.release();
+  c->ws_lat.release(); c->ws_list2.release(); c->ws_ert.release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   delete c;
 }
@@ -333,11 +333,11 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
 // shading of a batch of samples with the selected engine
 // ---------------------------------------------------------------------------------------------
 static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_mode, int slot, float* out5,
-                       uint8_t* valid_out, int engine, cudaStream_t st) {
+                       uint8_t* valid_out, int engine, cudaStream_t st, const ErtSegment& ert = ErtSegment{0, 0, nullptr, 0.0f}) {
   const bool use_tc = engine != 1 && c->tc_weights && tc_supported(c->scene_views, c->n_kpt, c->sp_level);
   KPN_CUDA(c, c->ws_list.reserve((size_t)n * sizeof(int)));
   int* counter = c->d_counters + slot;
-  KPN_CUDA(c, launch_compact(c->d_scene, src, n, query_mode, c->ws_list.as<int>(), counter, out5, valid_out, st));
+  KPN_CUDA(c, launch_compact(c->d_scene, src, n, query_mode, c->ws_list.as<int>(), counter, out5, valid_out, ert, st));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->profiling) {
     if (c->ev_used + 2 > c->ev_pool.size()) {
@@ -428,7 +428,7 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
   if (Rc < 128) Rc = 128;
   if (Rc > R) Rc = R;
   const long long nchunks = (R + Rc - 1) / Rc;
-  if (nchunks * 2 > MAX_CHUNKS) KPN_FAIL(c, KPN_ERR_ARG, "frame too large for one call (%lld chunks)", nchunks);
+  if (nchunks * 4 > MAX_CHUNKS) KPN_FAIL(c, KPN_ERR_ARG, "frame too large for one call (%lld chunks)", nchunks);
   KPN_CUDA(c, c->ws_rayd.reserve((size_t)Rc * 3 * sizeof(float)));
   KPN_CUDA(c, c->ws_raynf.reserve((size_t)Rc * 2 * sizeof(float)));
   KPN_CUDA(c, c->ws_z.reserve((size_t)Rc * Sc * sizeof(float)));
@@ -439,6 +439,23 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
   int rc = begin_counters(c, st);
   if (rc != KPN_OK) return rc;
   cudaMemcpyKind okind = host_out ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  // Shade the S samples of nr rays into ws_rgba.  Early-ray termination (ert_eps > 0, S >= 8): the front half of every ray is
+  // shaded and composited first; rays whose transmittance behind it is < ert_eps skip the back half (their remaining
+  // contribution to any channel is < ert_eps; the reference has no such option, ert_eps = 0 reproduces it exactly).
+  const bool ert_on = op->ert_eps > 0.0f;
+  if (ert_on) KPN_CUDA(c, c->ws_ert.reserve((size_t)Rc * sizeof(float)));
+  auto march = [&](const SampleSrc& src, int nr, int S, const float* zbuf, int slot) -> int {
+    const long long n = (long long)nr * S;
+    if (!ert_on || S < 8) return shade_batch(c, src, n, 0, slot, c->ws_rgba.as<float>(), nullptr, op->engine, st);
+    const int half = S / 2;
+    int r1 = shade_batch(c, src, n, 0, slot, c->ws_rgba.as<float>(), nullptr, op->engine, st, ErtSegment{0, half, nullptr, 0.0f});
+    if (r1 != KPN_OK) return r1;
+    KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), zbuf, 0, nr, S, half, nr, nullptr, nullptr, c->ws_ert.as<float>(), nullptr,
+                                 nullptr, st));
+    c->launches++;
+    return shade_batch(c, src, n, 0, slot + 1, c->ws_rgba.as<float>(), nullptr, op->engine, st,
+                       ErtSegment{half, S, c->ws_ert.as<float>(), op->ert_eps});
+  };
 
   for (long long ch = 0; ch < nchunks; ++ch) {
     const long long r0 = ch * Rc;
@@ -449,10 +466,10 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
     SampleSrc src;
     memset(&src, 0, sizeof(src));
     src.mode = 0; src.S = Sc; src.ray_d = c->ws_rayd.as<float>(); src.z = c->ws_z.as<float>(); src.o = d_o;
-    rc = shade_batch(c, src, (long long)nr * Sc, 0, (int)(2 * ch), c->ws_rgba.as<float>(), nullptr, op->engine, st);
+    rc = march(src, nr, Sc, c->ws_z.as<float>(), (int)(4 * ch));
     if (rc != KPN_OK) return rc;
     c->last_total += (unsigned long long)nr * Sc;
-    KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), c->ws_z.as<float>(), (int)r0, nr, Sc, R, dev[0], dev[1], dev[2],
+    KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), c->ws_z.as<float>(), (int)r0, nr, Sc, Sc, R, dev[0], dev[1], dev[2],
                                  nullptr, need_contrib ? c->ws_contrib.as<float>() : nullptr, st));
     c->launches++;
     if (out->contrib)
@@ -466,17 +483,17 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
         c->launches++;
       }
       src.S = Smax; src.z = c->ws_zfine.as<float>();
-      rc = shade_batch(c, src, (long long)nr * Smax, 0, (int)(2 * ch + 1), c->ws_rgba.as<float>(), nullptr, op->engine, st);
+      rc = march(src, nr, Smax, c->ws_zfine.as<float>(), (int)(4 * ch + 2));
       if (rc != KPN_OK) return rc;
       c->last_total += (unsigned long long)nr * Smax;
-      KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), c->ws_zfine.as<float>(), (int)r0, nr, Smax, R, dev[3], dev[4],
+      KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), c->ws_zfine.as<float>(), (int)r0, nr, Smax, Smax, R, dev[3], dev[4],
                                    dev[5], dev[6], nullptr, st));
       c->launches++;
       if (out->z_fine)
         KPN_CUDA(c, cudaMemcpyAsync(out->z_fine + r0 * Smax, c->ws_zfine.p, (size_t)nr * Smax * sizeof(float), okind, st));
     }
   }
-  c->counters_used = (int)(2 * nchunks);
+  c->counters_used = (int)(4 * nchunks);
   if (host_out) {
     for (int i = 0; i < 7; ++i)
       if (user[i]) KPN_CUDA(c, cudaMemcpyAsync(user[i], dev[i], (size_t)planes[i] * R * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -163,20 +163,29 @@ __global__ void coarse_z_kernel(const float* __restrict__ ray_nf, int nr, int S,
 // ------------------------------------------------------------------------------------------------
 // validity + compaction
 // ------------------------------------------------------------------------------------------------
+// Early-ray termination (ert.eps > 0, ray mode): only the samples s of a ray with ert.s_lo <= s < ert.s_hi are looked at (the
+// others keep what an earlier segment wrote), and a ray whose transmittance behind the earlier segments, 1 - ert.ray_alpha[ray],
+// is below ert.eps gets alpha = 0 entries instead of being shaded: what it could still add to the pixel is < eps per channel.
 __global__ void compact_kernel(const DevScene* __restrict__ sc, SampleSrc src, long long n, int query_mode,
                                int* __restrict__ list, int* __restrict__ counter, float* __restrict__ out5,
-                               uint8_t* __restrict__ valid_out) {
+                               uint8_t* __restrict__ valid_out, ErtSegment ert) {
   const DevScene& S = *sc;
   __shared__ int s_cnt[8];
   __shared__ int s_base;
   for (long long base = (blockIdx.x * (long long)blockDim.x) ; base < n; base += (long long)gridDim.x * blockDim.x) {   // block-uniform trip count
     long long i = base + threadIdx.x;
     bool ok = false;
-    if (i < n) {
+    bool in_seg = i < n;
+    if (in_seg && ert.s_hi > 0) {
+      const int sidx = (int)(i % src.S);
+      in_seg = sidx >= ert.s_lo && sidx < ert.s_hi;
+    }
+    if (in_seg) {
       float p[3], d[3];
       Proj q[MAXV];
       fetch_sample(src, i, p, d);
       ok = sample_valid(S, p, q);
+      if (ok && ert.ray_alpha != nullptr && 1.0f - ert.ray_alpha[i / src.S] < ert.eps) ok = false;   // ray already opaque
       if (!ok) {
         float* o = out5 + 5 * i;
         if (query_mode) { o[0] = 0.f; o[1] = 0.f; }
@@ -544,7 +553,7 @@ shade_simt_kernel(const DevScene* __restrict__ scp, const DevWeightsF32* __restr
 // One WARP per ray: lane l takes samples l, l+32, ... (coalesced reads), the transmittance T_k = prod_{j<k} (1 - a_j) is an
 // exclusive product scan across the lanes carried from one group of 32 samples to the next, the ray sums are warp reductions.
 __global__ void __launch_bounds__(128)
-composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, int r0, int nr, int S,
+composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, int r0, int nr, int S, int S_eval,
                  long long plane, float* __restrict__ color, float* __restrict__ depth,
                  float* __restrict__ alpha, float* __restrict__ sdf, float* __restrict__ contrib) {
   const int lane = threadIdx.x & 31;
@@ -554,10 +563,10 @@ composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, in
     const float* zz = z + (long long)i * S;
     float Tc = 1.0f;   // transmittance in front of this group of 32 samples
     float acc = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f, cs = 0.0f;
-    for (int k0 = 0; k0 < S; k0 += 32) {
+    for (int k0 = 0; k0 < S_eval; k0 += 32) {   // S_eval < S: composite of the first S_eval samples only (ERT segment)
       const int k = k0 + lane;
       float a = 0.0f, zk = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f, q4 = 0.0f;
-      if (k < S) {
+      if (k < S_eval) {
         zk = zz[k];
         const float dist = k + 1 < S ? zz[k + 1] - zk : 1e10f;
         a = 1.0f - expf(-q[5 * k] * dist);
@@ -573,7 +582,7 @@ composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, in
       if (lane == 0) ex = 1.0f;
       const float c = a * (Tc * ex);
       Tc *= __shfl_sync(0xffffffffu, p, 31);
-      if (k < S) {
+      if (k < S_eval) {
         acc += c; cr += c * q2; cg += c * q3; cb += c * q4; cd += c * zk; cs += c * q1;
         if (contrib) contrib[(long long)i * S + k] = c;
       }
@@ -667,8 +676,8 @@ cudaError_t launch_coarse_z(const float* ray_nf, int nr, int S, float* z, cudaSt
   return cudaGetLastError();
 }
 cudaError_t launch_compact(const DevScene* sc, const SampleSrc& src, long long n, int query_mode, int* list, int* counter,
-                           float* out5, uint8_t* valid_out, cudaStream_t st) {
-  compact_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(sc, src, n, query_mode, list, counter, out5, valid_out);
+                           float* out5, uint8_t* valid_out, const ErtSegment& ert, cudaStream_t st) {
+  compact_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(sc, src, n, query_mode, list, counter, out5, valid_out, ert);
   return cudaGetLastError();
 }
 cudaError_t launch_shade_simt(const DevScene* sc, const DevWeightsF32* W, const SampleSrc& src, const int* list,
@@ -684,9 +693,9 @@ cudaError_t launch_shade_simt(const DevScene* sc, const DevWeightsF32* W, const 
   shade_simt_kernel<<<grid, NT, SHADE_SMEM_BYTES, st>>>(sc, W, src, list, counter, query_mode, out5);
   return cudaGetLastError();
 }
-cudaError_t launch_composite(const float* rgba, const float* z, int r0, int nr, int S, long long plane, float* color,
+cudaError_t launch_composite(const float* rgba, const float* z, int r0, int nr, int S, int S_eval, long long plane, float* color,
                              float* depth, float* alpha, float* sdf, float* contrib, cudaStream_t st) {
-  composite_kernel<<<grid_for((long long)nr * 32, 128, 148 * 64), 128, 0, st>>>(rgba, z, r0, nr, S, plane, color, depth, alpha, sdf, contrib);
+  composite_kernel<<<grid_for((long long)nr * 32, 128, 148 * 64), 128, 0, st>>>(rgba, z, r0, nr, S, S_eval, plane, color, depth, alpha, sdf, contrib);
   return cudaGetLastError();
 }
 cudaError_t launch_importance(const float* contrib, const float* z, int nr, int Sc, int Sf, float* zout, cudaStream_t st) {

@@ -11,11 +11,11 @@ cudaError_t launch_prep_target(const RawTarget* raw, DevTarget* tg, cudaStream_t
 cudaError_t launch_rays(const DevScene* sc, const DevTarget* tg, int r0, int nr, float* ray_d, float* ray_nf, cudaStream_t st);
 cudaError_t launch_coarse_z(const float* ray_nf, int nr, int S, float* z, cudaStream_t st);
 cudaError_t launch_compact(const DevScene* sc, const SampleSrc& src, long long n, int query_mode, int* list, int* counter,
-                           float* out5, uint8_t* valid_out, cudaStream_t st);
+                           float* out5, uint8_t* valid_out, const ErtSegment& ert, cudaStream_t st);
 cudaError_t launch_shade_simt(const DevScene* sc, const DevWeightsF32* W, const SampleSrc& src, const int* list,
                               const int* counter, long long n_max, int query_mode, float* out5, int num_sms,
                               cudaStream_t st);
-cudaError_t launch_composite(const float* rgba, const float* z, int r0, int nr, int S, long long plane, float* color,
+cudaError_t launch_composite(const float* rgba, const float* z, int r0, int nr, int S, int S_eval, long long plane, float* color,
                              float* depth, float* alpha, float* sdf, float* contrib, cudaStream_t st);
 cudaError_t launch_importance(const float* contrib, const float* z, int nr, int Sc, int Sf, float* zout, cudaStream_t st);
 // Tensor-core engine: geometry+density kernel (CTA pairs), then the colour kernel on the samples with density > 0.

@@ -76,6 +76,13 @@ struct SampleSrc {
   const float* o;      // (3) ray origin on device (mode 0)
 };
 
+// Segment of a ray's samples handled by one compaction pass of an early-ray-termination render (s_hi == 0: all samples).
+struct ErtSegment {
+  int s_lo, s_hi;
+  const float* ray_alpha;   // accumulated alpha of the earlier segments per ray of the chunk, or nullptr
+  float eps;
+};
+
 enum Layer {
   L_GEO0 = 0, L_GEO1, L_GEO2, L_GEO3, L_DEN0, L_DEN1, L_DEN2, L_CMP,
   L_RE0, L_RE1, L_BASE0, L_BASE1, L_VIS1A, L_VIS1B, L_VIS2A, L_VIS2B, L_OUT0, L_OUT1, L_OUT2

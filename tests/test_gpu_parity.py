@@ -383,3 +383,39 @@ def test_24_keypoint_frame_many_tiles_per_slot():
     e_rob = float(err[~flipped].max())
     print(f"24-keypoint 192^2x96 frame, tcgen05 vs fp32 engine: max rgb err {e_rob:.2e}, flipped {float(flipped.float().mean()):.4%}")
     assert e_rob < 1e-3 and float(flipped.float().mean()) < 0.01
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_early_ray_termination(engine):
+    """ert_eps > 0 (BASELINE config 3): the front half of every ray is composited first and rays that are already opaque
+    skip their back half.  Dense scene (density gain x600) so that many rays saturate early.  Properties: (1) every output
+    stays within ert_eps (+ round-off) of the exact render, coarse and fine; (2) fewer samples are shaded; (3) ert_eps = 0
+    is the exact path (bit-identical to not passing it)."""
+    eps = 1e-3
+    scene = syn.make_scene(src_size=256, n_kpt=18)
+    weights = syn.make_weights(18, density_gain=600.0)
+    target = syn.make_target(size=128)
+    net = build_model(weights, 18, "cuda:0")
+    a = scene_tensors(scene, target, "cuda:0")
+    m = net._bind_scene(a["cam"], a["feat_geo"], a["feat_tex"], a["sp_data"], a["img"], a["fg"], a["bounds"])
+    kw = dict(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=128, ny=128, S_c=48, S_f=32,
+              fine=True, engine=engine)
+    exact = m.render(**kw)
+    n_exact = m.stats()["samples_valid"]
+    zero = m.render(ert_eps=0.0, **kw)
+    ert = m.render(ert_eps=eps, **kw)
+    n_ert = m.stats()["samples_valid"]
+    torch.cuda.synchronize()
+    for k in ("tex_fg", "alpha", "tex_fg_fine", "alpha_fine"):
+        assert torch.equal(exact[k], zero[k])
+    saturated = float((exact["alpha"] > 1.0 - eps).float().mean())
+    d_c = float((ert["tex_fg"] - exact["tex_fg"]).abs().max())
+    d_a = float((ert["alpha"] - exact["alpha"]).abs().max())
+    print(f"ERT engine {engine}: coarse rgb diff {d_c:.2e} alpha diff {d_a:.2e}; shaded samples {n_ert}/{n_exact} "
+          f"({n_ert / n_exact:.3f}); opaque rays {saturated:.3f}")
+    assert saturated > 0.05, "scene not dense enough to exercise early termination"
+    assert d_c <= eps * 1.05 + 1e-5 and d_a <= eps * 1.05 + 1e-5
+    assert n_ert < 0.97 * n_exact
+    # the fine pass resamples from the (slightly different) coarse weights: robust comparison as for the free-running fine pass
+    q = float(torch.quantile((ert["tex_fg_fine"] - exact["tex_fg_fine"]).abs().flatten().float().cpu(), 0.99))
+    assert q <= 5e-3
