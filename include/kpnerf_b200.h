@@ -172,6 +172,10 @@ int kpn_get_stats(kpn_ctx* ctx, kpn_stats* stats, void* stream);
  * flag afterwards.  kpn_get_stats reports a raised flag as KPN_ERR_CUDA.  Synchronises the device. */
 int kpn_debug_timing(kpn_ctx* ctx, int enable, unsigned long long* out16);
 
+/* Host-only test hook (no GPU needed): tensor-core engine's input permutation of geometry stage `stage` (0..5) for n_kpt in
+ * {18, 24}: kmap_out[i] = K index input i is multiplied with, *kbias_out = K index of the bias row, *kpad_out = padded K. */
+int kpn_debug_kmap(int stage, int n_kpt, int n_inputs, int* kmap_out, int* kbias_out, int* kpad_out);
+
 /* enable != 0: bracket every shading-kernel launch with CUDA events on its stream (no sync). */
 int kpn_set_profiling(kpn_ctx* ctx, int enable);
 

@@ -17,7 +17,7 @@ KPN_MEM_HOST = 1
 KPN_NUM_LAYERS = 19
 
 EXPORTS = ["kpn_abi_version", "kpn_create", "kpn_destroy", "kpn_last_error", "kpn_set_weights", "kpn_set_scene",
-           "kpn_render", "kpn_query", "kpn_get_stats", "kpn_set_profiling", "kpn_selftest_umma", "kpn_selftest_umma2", "kpn_debug_timing"]
+           "kpn_render", "kpn_query", "kpn_get_stats", "kpn_set_profiling", "kpn_selftest_umma", "kpn_selftest_umma2", "kpn_debug_timing", "kpn_debug_kmap"]
 
 c_float_p = C.POINTER(C.c_float)
 c_u8_p = C.POINTER(C.c_uint8)
@@ -102,6 +102,8 @@ def load() -> C.CDLL:
     lib.kpn_set_profiling.restype = C.c_int
     lib.kpn_debug_timing.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.kpn_debug_timing.restype = C.c_int
+    lib.kpn_debug_kmap.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.kpn_debug_kmap.restype = C.c_int
     lib.kpn_selftest_umma2.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.kpn_selftest_umma2.restype = C.c_int
     lib.kpn_selftest_umma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

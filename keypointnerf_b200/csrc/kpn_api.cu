@@ -73,7 +73,6 @@ struct kpn_ctx {
   DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in, ws_lat, ws_list2, ws_ert;
   unsigned long long launches = 0;
   bool profiling = false;
-  unsigned long long* d_timing = nullptr;   // [16] debug: per-stage wait cycles of the tensor-core row warps
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   size_t ev_used = 0;
 };
@@ -243,7 +242,6 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
     bias(L_VIS2A, T.b_vis2a); bias(L_OUT0, T.b_out0);
     for (int o = 0; o < 2; ++o) { for (int i = 0; i < 64; ++i) T.w_p2[o][i] = We[L_DEN2][o * 64 + i]; T.b_p2[o] = w->layer[L_DEN2].bias[o]; }
     for (int o = 0; o < 16; ++o) { for (int i = 0; i < 4; ++i) T.w_re0[o][i] = We[L_RE0][o * 4 + i]; T.b_re0[o] = w->layer[L_RE0].bias[o]; }
-    for (int o = 0; o < 35; ++o) { for (int i = 0; i < 16; ++i) T.w_re1[o][i] = We[L_RE1][o * 16 + i]; T.b_re1[o] = w->layer[L_RE1].bias[o]; }
     for (int i = 0; i < 32; ++i) T.w_vis2b[i] = We[L_VIS2B][i];
     T.b_vis2b = w->layer[L_VIS2B].bias[0];
     for (int o = 0; o < 8; ++o) { for (int i = 0; i < 16; ++i) T.w_out1[o][i] = We[L_OUT1][o * 16 + i]; T.b_out1[o] = w->layer[L_OUT1].bias[o]; }
@@ -355,7 +353,7 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_
     KPN_CUDA(c, c->ws_list2.reserve((size_t)n * 8));
     KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), c->wlo.as<uint8_t>(), engine == 2 ? 0 : 1, c->n_kpt,
                                 src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->ws_lat.p, c->ws_list2.p,
-                                c->d_counters2 + slot, c->num_sms, st, c->d_timing));
+                                c->d_counters2 + slot, c->num_sms, st));
     c->launches++;
   }
   else
@@ -584,6 +582,16 @@ extern "C" int kpn_debug_timing(kpn_ctx* c, int enable, unsigned long long* out1
   unsigned int wd[8];
   KPN_CUDA(c, tc_watchdog_read(wd, enable != 0));
   if (out16) { for (int i = 0; i < 16; ++i) out16[i] = i < 8 ? wd[i] : 0ull; }
+  return KPN_OK;
+}
+
+// Host-only test hook: the K index (element of the fp16 activation row) each input of a geometry stage is multiplied with, and
+// the K index of its bias row (tests/test_host_abi.py checks that the layer-0 permutation is a bijection).
+extern "C" int kpn_debug_kmap(int stage, int n_kpt, int n_inputs, int* kmap_out, int* kbias_out, int* kpad_out) {
+  if (stage < 0 || stage > 5 || !tc_supported(3, n_kpt, 3) || n_inputs < 0 || !kmap_out) return KPN_ERR_ARG;
+  for (int i = 0; i < n_inputs; ++i) kmap_out[i] = tc_kmap(stage, n_kpt, i);
+  if (kbias_out) *kbias_out = tc_kbias(stage, n_kpt);
+  if (kpad_out) *kpad_out = make_tc_plan(n_kpt).st[stage].Kp;
   return KPN_OK;
 }
 

@@ -23,8 +23,7 @@ cudaError_t launch_importance(const float* contrib, const float* z, int nr, int 
 // geometry stages; lat_scratch: n_max x 48 bytes, list2: n_max x int2, count2: device int (zeroed by the caller).
 cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term, int n_kpt,
                             const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
-                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st,
-                            unsigned long long* timing = nullptr);
+                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st);
 size_t tc_pair_blob_bytes(int n_kpt);
 cudaError_t tc_watchdog_read(unsigned int out[8], bool reset);
 size_t tc_weight_blob_bytes(int n_kpt);

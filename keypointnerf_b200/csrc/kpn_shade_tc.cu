@@ -1127,7 +1127,7 @@ bool tc_supported(int n_views, int n_kpt, int sp_level) { return n_views == 3 &&
 template <int NK>
 static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term,
                                   const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
-                                  uint4* lat, int2* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
+                                  uint4* lat, int2* list2, int* count2, int num_sms, cudaStream_t st) {
   constexpr TcPlan plan = make_tc_plan(NK);
   const size_t smem_geo = plan.st[GEO_NSTAGE].off + (geo_pref(NK) ? (size_t)NSLOT * GEO_FW * 128 * 4 : 0);
   const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
@@ -1159,12 +1159,12 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
 
 cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term, int n_kpt,
                             const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
-                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st, unsigned long long* timing) {
+                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st) {
   if (n_kpt == 18)
     return launch_tc_impl<18>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
-                              (int2*)list2, count2, num_sms, st, timing);
+                              (int2*)list2, count2, num_sms, st);
   return launch_tc_impl<24>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
-                            (int2*)list2, count2, num_sms, st, timing);
+                            (int2*)list2, count2, num_sms, st);
 }
 
 // Watchdog state of this module's kernels: out[0] != 0 -> some barrier wait gave up at block out[1], thread out[2], tag out[3].

@@ -79,8 +79,7 @@ __host__ __device__ constexpr TcPlan make_tc_plan(int n_kpt) {
 // them as constant-bank operands.
 struct TcConsts {
   float w_p2[2][64], b_p2[2];          // density head last layer (fp32 on CUDA cores); the geometry-stage biases ride in the MMAs
-  float w_re0[16][4], b_re0[16];       // ray-direction encoder
-  float w_re1[35][16], b_re1[35];
+  float w_re0[16][4], b_re0[16];       // ray-direction encoder, first layer (the second runs on the tensor core, stage 12)
   float b_base0[64], b_base1[32], b_vis1a[32], b_vis1b[48], b_vis2a[32];
   float w_vis2b[32], b_vis2b;
   float b_out0[16];

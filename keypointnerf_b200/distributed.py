@@ -77,3 +77,13 @@ def gather_views(frame: torch.Tensor, world: int) -> torch.Tensor:
     if world == 1:
         return frame[None]
     return _all_gather_stack(frame, world)
+
+
+def render_frame_row_sharded(marcher, *, K, RT, znear, zfar, width: int, height: int, rank: int, world: int, **render_kw) -> dict:
+    """BASELINE config 4: ONE target frame split into contiguous row bands, one band per rank (the scene must already be bound
+    to every rank's ``RayMarcher``), then one all-gather per output plane.  ``render_kw`` goes to ``RayMarcher.render``
+    (``S_c``, ``S_f``, ``fine``, ``engine``, ``ert_eps``).  Returns full-frame tensors on every rank, bit-identical to the
+    single-GPU frame because rays are independent (``tests/test_gpu_parity.py`` checks strided/offset passes against the frame)."""
+    y0, ny = row_shard(height, rank, world)
+    res = marcher.render(K=K, RT=RT, znear=znear, zfar=zfar, x0=0, y0=y0, step=1, nx=width, ny=ny, out_device="cuda", **render_kw)
+    return {k: gather_rows(v, height, rank, world) for k, v in res.items() if v.dim() >= 2 and v.shape[-2] == ny}

@@ -340,6 +340,14 @@ def test_full_frame_properties_at_baseline_size():
     torch.cuda.synchronize()
     assert torch.equal(frame["tex_fg"][:, 5::8, 3::8], tile["tex_fg"])
     assert torch.equal(frame["alpha"][5::8, 3::8], tile["alpha"])
+    # BASELINE config 4's partition: a row band rendered on its own (what one rank of a row-sharded frame does) is the
+    # corresponding slice of the frame, and the sharded entry point with world = 1 is the frame itself
+    from keypointnerf_b200 import distributed as D
+    y0, ny = D.row_shard(512, 3, 8)
+    band = m.render(x0=0, y0=y0, step=1, nx=512, ny=ny, **kw)
+    assert torch.equal(frame["tex_fg"][:, y0:y0 + ny], band["tex_fg"]) and torch.equal(frame["alpha"][y0:y0 + ny], band["alpha"])
+    whole = D.render_frame_row_sharded(m, width=512, height=512, rank=0, world=1, **kw)
+    assert torch.equal(whole["tex_fg"], frame["tex_fg"])
     al = frame["alpha"]
     assert float(al.min()) >= 0.0 and float(al.max()) <= 1.0 + 1e-5
     assert float(frame["tex_fg"].min()) >= -1e-6 and float(frame["tex_fg"].max()) <= 1.0 + 1e-5

@@ -91,3 +91,27 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("n_kpt", [18, 24])
+def test_tensor_core_input_permutation_is_a_bijection(lib, n_kpt):
+    """Geometry-stage weight packing (host code of the library, no GPU): every input of a stage is multiplied with its own K
+    index, the bias row has a K index of its own, everything fits the padded K; layer 0 additionally keeps the two column runs
+    (thread 0 | thread 1) 8-column aligned as the tensor-memory stores of the kernel require."""
+    n_in = {0: 7 * n_kpt + 64, 1: 128, 2: 136, 3: 120, 4: 128, 5: 64}
+    for stage, n in n_in.items():
+        kmap = (C.c_int * n)()
+        kbias, kpad = C.c_int(), C.c_int()
+        assert lib.kpn_debug_kmap(stage, n_kpt, n, kmap, C.byref(kbias), C.byref(kpad)) == 0
+        ks = list(kmap)
+        assert len(set(ks)) == n and kbias.value not in ks
+        assert 0 <= min(ks) and max(ks + [kbias.value]) < kpad.value and kpad.value % 16 == 0
+    # layer 0: encoding element (r, k) of keypoint pair j = k // 2 sits at packed column 7 j' + r, pairs of one thread contiguous
+    kmap = (C.c_int * (7 * n_kpt + 64))()
+    lib.kpn_debug_kmap(0, n_kpt, 7 * n_kpt + 64, kmap, None, None)
+    cols = np.array(kmap) // 2
+    for k in range(0, n_kpt, 2):
+        pair_cols = sorted(cols[r * n_kpt + k] for r in range(7))
+        assert pair_cols == list(range(pair_cols[0], pair_cols[0] + 7))
+        assert all(cols[r * n_kpt + k] == cols[r * n_kpt + k + 1] for r in range(7))   # the two keypoints of a pair share columns
+    assert lib.kpn_debug_kmap(0, 20, 4, kmap, None, None) != 0   # unsupported keypoint count
