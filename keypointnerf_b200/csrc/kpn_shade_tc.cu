@@ -1131,13 +1131,15 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   constexpr TcPlan plan = make_tc_plan(NK);
   const size_t smem_geo = plan.st[GEO_NSTAGE].off + (geo_pref(NK) ? (size_t)NSLOT * GEO_FW * 128 * 4 : 0);
   const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};   // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
     cudaError_t e = cudaFuncSetAttribute(shade_geo_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_geo);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(shade_color_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col);
     if (e != cudaSuccess) return e;
-    attr = true;
+    if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   const long long max_tiles = (n_max + SPT - 1) / SPT;
   long long pairs = (max_tiles + 2 * NSLOT - 1) / (2 * NSLOT);   // clusters that can have work
