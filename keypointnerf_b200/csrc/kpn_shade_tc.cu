@@ -1,28 +1,28 @@
 // Ray-march shading, engine 0: tcgen05 tensor-core MLPs with activations resident in tensor memory.
 //
-// Two persistent kernels per batch of valid samples (one CTA per SM each):
+// Two persistent kernels per batch of valid samples:
 //   shade_geo_kernel   : gather + keypoint encoding + geometry MLP (L0-L3) + view pooling + density tail (P0|compress, P1,
 //                        64->2 head).  Writes alpha/sdf per sample, the 24-wide compressed latent (fp16) to a scratch buffer,
 //                        and appends the samples that need a colour (density > 0; every valid sample in query mode) to a
 //                        second work list.  A sample with alpha == 0 has compositing weight exactly 0 (src/model.py:1167),
-//                        so skipping its colour is exact.
-//   shade_color_kernel : IBR colour head (BASE0, BASE1, VIS1A, VIS1B, VIS2A, OUT0 on tensor cores; ray encoder, 32->1,
-//                        16->8->1 in fp32 on CUDA cores) for the second list.
-// Common structure: 4 "row" warps per tile slot, a row = one (sample, source view) pair, the 3 views of a sample in 3
-// adjacent lanes (10 samples per warp, 40 per tile) so every cross-view reduction of the reference (view pooling,
-// src/utils.py:722-748; blending weights, mean/var, softmax, src/model.py:1286-1301) is a 3-lane shuffle.  Each row thread
-// owns TMEM lane = its row: it writes its layer input as packed fp16 straight into tensor memory (tcgen05.st), an issuer
-// thread multiplies it with fp16 weights resident in shared memory (bulk-TMA loaded once per CTA) into an fp32 accumulator in
-// the slot's other column region, tcgen05.commit -> mbarrier -> the row thread reads its accumulator row (tcgen05.ld), applies
-// bias + activation in fp32 and overwrites it in place with the next layer's fp16 input.  Activations never touch shared or
-// global memory.  Slots ping-pong so the tensor pipe works on one tile while the CUDA cores run another's epilogue:
-//   geo kernel  : 2 slots x 256 TMEM columns (regions R0/R1 of 128), + one W_lo issuer per slot (see "Precision" below);
-//   colour kernel: 3 slots x 128 TMEM columns (regions of 64).
-// Stage table (A region -> D region):
-//   geo   0 L0 190->128 R0->R1 | 1 L1 128->128 R1->R0 | 2 L2 136->120 R0->R1 | 3 L3 120->64 R1->R0
-//         4 P0|CMP 128->64|24 R1->R0 | 5 P1 64->64 R0->R1
-//   colour 6 BASE0 105->64 R0->R1 | 7 BASE1 64->32 R1->R0 | 8 VIS1A 32->32 R0->R1 | 9 VIS1B 32->33 R1->R0
-//         10 VIS2A 32->32 R0->R1 | 11 OUT0 37->16 R1->R0
+//                        so skipping its colour is exact.  CTA pairs (cta_group::2), 16 row warps per CTA (2 tile slots x 4
+//                        TMEM lane quarters x 2 column halves), no control warp; see the block comment above geo_dcol.
+//   shade_color_kernel : IBR colour head (RE1, BASE0, BASE1, VIS1A, VIS1B, VIS2A, OUT0 on tensor cores; first ray-encoder
+//                        layer, 32->1, 16->8->1 in fp32 on CUDA cores) for the second list.  One CTA per SM, 3 tile slots x 4
+//                        row warps + an issuer warp.
+// Common structure: a row = one (sample, source view) pair, the 3 views of a sample in 3 adjacent lanes (10 samples per
+// warp, 40 per tile) so every cross-view reduction of the reference (view pooling, src/utils.py:722-748; blending weights,
+// mean/var, softmax, src/model.py:1286-1301) is a 3-lane shuffle.  A row thread owns TMEM lane = its row: it writes its layer
+// input as packed fp16 straight into tensor memory (tcgen05.st), the slot's issuer multiplies it with fp16 weights resident
+// in shared memory (bulk-TMA loaded once per CTA) into an fp32 accumulator in another column region, tcgen05.commit ->
+// mbarrier -> the row thread reads its accumulator columns (tcgen05.ld), applies the activation and writes the next layer's
+// fp16 input.  Activations never touch shared or global memory.  Slots ping-pong so the tensor pipe works on one tile while
+// the CUDA cores run another's epilogue.
+// Stage table:
+//   geo    0 L0 190->128 | 1 L1 128->128 | 2 L2 136->120 | 3 L3 120->64 | 4 P0|CMP 128->64|24 | 5 P1 64->64
+//          (biases as K rows, two-term weights W_hi + W_lo; tensor-memory placement: geo_dcol)
+//   colour 12 RE1 16->35 R0->R1 | 6 BASE0 105->64 R0->R1 | 7 BASE1 64->32 R1->R0 | 8 VIS1A 32->32 R0->R1 | 9 VIS1B 32->33 R1->R0
+//          10 VIS2A 32->32 R0->R1 | 11 OUT0 37->16 R1->R0     (R0/R1: the slot's two 64-column regions, in-place epilogues)
 #include <cstdlib>
 #include "kpn_device.cuh"
 #include "kpn_launch.h"
