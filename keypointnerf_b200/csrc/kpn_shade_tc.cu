@@ -8,8 +8,8 @@
 //                        so skipping its colour is exact.  CTA pairs (cta_group::2), 16 row warps per CTA (2 tile slots x 4
 //                        TMEM lane quarters x 2 column halves), no control warp; see the block comment above geo_dcol.
 //   shade_color_kernel : IBR colour head (RE1, BASE0, BASE1, VIS1A, VIS1B, VIS2A, OUT0 on tensor cores; first ray-encoder
-//                        layer, 32->1, 16->8->1 in fp32 on CUDA cores) for the second list.  One CTA per SM, 3 tile slots x 4
-//                        row warps + an issuer warp.
+//                        layer, 32->1, 16->8->1 in fp32 on CUDA cores) for the second list.  One CTA per SM, 4 tile slots x 4
+//                        row warps (row warp 0 of a slot issues its MMAs).
 // Common structure: a row = one (sample, source view) pair, the 3 views of a sample in 3 adjacent lanes (10 samples per
 // warp, 40 per tile) so every cross-view reduction of the reference (view pooling, src/utils.py:722-748; blending weights,
 // mean/var, softmax, src/model.py:1286-1301) is a 3-lane shuffle.  A row thread owns TMEM lane = its row: it writes its layer
@@ -34,9 +34,9 @@ namespace {
 
 constexpr int ROW_WARPS = 4;
 constexpr int NSLOT = 2;                                  // geo kernel tile slots
-constexpr int CSLOT = 3;                                  // colour kernel tile slots
-constexpr int TCC_THREADS = (CSLOT * ROW_WARPS + 1) * 32; // 416: 12 row warps + issuer
-constexpr int GEO_NSTAGE = 6, COL_NSTAGE = 7;   // colour: RE1 (stage 12) then stages 6..11
+constexpr int CSLOT = 4;                                  // colour kernel tile slots (4 x 128 TMEM columns)
+constexpr int TCC_THREADS = CSLOT * ROW_WARPS * 32;       // 512: 16 row warps, row warp 0 of a slot issues its MMAs
+constexpr int GEO_NSTAGE = 6;   // colour kernel: RE1 (stage 12), then stages 6..11
 constexpr int SPW = 10;                                   // samples per warp (3 views each)
 constexpr int SPT = SPW * ROW_WARPS;                      // samples per tile
 constexpr float LOG2E = 1.4426950408889634f;
@@ -105,6 +105,9 @@ struct RowCtx {
   uint32_t ph;          // parity of acc_ready this thread waits on next
   int gb;               // first lane of this row's 3-view group
   int l1, l2;           // the other two lanes of the group
+  int issuer;           // this warp issues the slot's MMAs (row warp 0 of the slot); no dedicated issuer warp
+  uint32_t pha;         // parity of a_ready the issuer waits on next
+  uint32_t slot_tm, wlo0, el;
 };
 
 // The activation tile lives in tensor memory: tcgen05.wait::st + tcgen05.fence::before_thread_sync order it, so the arrive
@@ -667,6 +670,10 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
 }
 
 // Colour pass for one tile of the second work list (entries: x = slot of the latent in the scratch buffer, y = sample id).
+template <int NK, int STAGE>
+__device__ __forceinline__ void col_mma(RowCtx& c);
+
+template <int NK>
 __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, const SampleSrc& src,
                                            const int2* __restrict__ list2, int count, int tile, RowCtx& cx, int roww, int lane,
                                            const uint4* __restrict__ lat_in, float* __restrict__ out5) {
@@ -728,6 +735,7 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
     for (int i = 9; i < 16; ++i) a[i] = 0u;
     tc::tmem_st16(R0, a);
     signal_a(cx);
+    col_mma<NK, 12>(cx);
     wait_acc(cx);
     uint32_t r[32], r2[8];
     tc::tmem_ld32(R1, r);
@@ -767,10 +775,12 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
     tc::tmem_st8(R0 + 48, a + 48);
   }
   signal_a(cx);
+  col_mma<NK, 6>(cx);
   // ---- BASE0 -> BASE1
   wait_acc(cx);
   epi_inplace<2, 2>(R1, R1, C.b_base0);
   signal_a(cx);
+  col_mma<NK, 7>(cx);
   wait_acc(cx);
   float x[32];
   {
@@ -785,10 +795,12 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
     tc::tmem_st16(R0, o);
   }
   signal_a(cx);
+  col_mma<NK, 8>(cx);
   // ---- VIS1A -> VIS1B (src/model.py:1294-1296)
   wait_acc(cx);
   epi_inplace<1, 2>(R1, R1, C.b_vis1a);
   signal_a(cx);
+  col_mma<NK, 9>(cx);
   wait_acc(cx);
   {
     uint32_t r[32], r2[16];
@@ -804,6 +816,7 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
     tc::tmem_st16(R0, o);
   }
   signal_a(cx);
+  col_mma<NK, 10>(cx);
   // ---- VIS2A (+ 32->1 sigmoid on CUDA cores) -> OUT0 input [x32 | vis | ray_diff4 | 0-pad] (src/model.py:1297-1300)
   wait_acc(cx);
   {
@@ -826,6 +839,7 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
     tc::tmem_st8(R1 + 16, o + 16);
   }
   signal_a(cx);
+  col_mma<NK, 11>(cx);
   // ---- OUT0 -> 16->8->1 on CUDA cores -> softmax over the views -> blended colour (src/model.py:1300-1301)
   wait_acc(cx);
   float logit;
@@ -916,6 +930,18 @@ __device__ __forceinline__ void col_issue(uint32_t slot_tm, uint32_t wlo0, uint3
   const uint32_t b0 = wlo0 + ((plan.st[STAGE].off - plan.st[GEO_NSTAGE].off) >> 4) + ((lbo >> 4) << 16);
 #pragma unroll
   for (int j = 0; j < Kp / 16; ++j) tc::mma_ts_el(d_tm, a_tm + (uint32_t)j * 8u, b0 + (uint32_t)j * step, dhi, idesc, j > 0 ? 1u : 0u, el);
+}
+
+// issuer warp only: once the slot's four row warps have signalled this stage's input, issue its MMAs and commit
+template <int NK, int STAGE>
+__device__ __forceinline__ void col_mma(RowCtx& c) {
+  if (c.issuer) {
+    tc::mbar_wait(c.a_ready, c.pha, 0x50u + (uint32_t)STAGE);
+    c.pha ^= 1u;
+    tc::fence_after_sync();
+    col_issue<NK, STAGE>(c.slot_tm, c.wlo0, c.el);
+    tc::mma_commit_el(c.acc_ready, c.el);
+  }
 }
 
 __device__ __forceinline__ void stage_scene(SceneS& scs, const DevScene& g, int NK, int t, int nthreads) {
@@ -1043,63 +1069,23 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
   __shared__ SceneS scs;
   constexpr TcPlan plan = make_tc_plan(NK);
   constexpr uint32_t OFF0 = plan.st[GEO_NSTAGE].off, WBYTES = plan.total_bytes - plan.st[GEO_NSTAGE].off;
-  constexpr int ISSUER = CSLOT * ROW_WARPS;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int count = *count_ptr;
   const int ntiles = (count + SPT - 1) / SPT;
   stage_scene(scs, *scp, NK, t, TCC_THREADS);
-  if (warp == ISSUER) tc::tmem_alloc(&tmem_base_s, 512);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (t == 0) {
     tc::mbar_init(&bars[0], 1);
     for (int s = 0; s < CSLOT; ++s) { tc::mbar_init(&bars[1 + 2 * s], ROW_WARPS); tc::mbar_init(&bars[2 + 2 * s], 1); }
     tc::fence_mbar_init();
   }
+  __syncthreads();
+  if (t == 0 && ntiles > 0) load_weights(wsm, wblob + OFF0, WBYTES, &bars[0]);   // the colour stages' weight tiles, once per CTA
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
-  auto tiles_of_slot = [&](int s) {
-    int n = 0;
-    for (int tile = blockIdx.x * CSLOT + s; tile < ntiles; tile += gridDim.x * CSLOT) ++n;
-    return n;
-  };
-  if (warp == ISSUER) {
-    if (ntiles > 0) {      // the whole warp runs the loop, one elected lane issues
-      if (lane == 0) load_weights(wsm, wblob + OFF0, WBYTES, &bars[0]);
-      __syncwarp();
-      const uint32_t el = tc::elect_one();
-      const uint32_t wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu;
-      int remaining[CSLOT], stage[CSLOT], left = 0;
-      uint32_t par[CSLOT];
-      for (int s = 0; s < CSLOT; ++s) { remaining[s] = tiles_of_slot(s) * COL_NSTAGE; stage[s] = 0; par[s] = 0; left += remaining[s]; }
-      uint32_t idle = 0;
-      while (left > 0) {
-        if ((++idle & 1023u) == 0u && tc::wd_give_up(idle, 1u << 24, 0x40u, 0u)) break;
-#pragma unroll
-        for (int s = 0; s < CSLOT; ++s) {
-          if (remaining[s] > 0 && __all_sync(FULL, tc::mbar_test_wait(&bars[1 + 2 * s], par[s]))) {
-            idle = 0;
-            tc::fence_after_sync();
-            const uint32_t stm = tbase + (uint32_t)s * 128u;
-            switch (stage[s]) {
-              case 0: col_issue<NK, 12>(stm, wlo0, el); break;
-              case 1: col_issue<NK, 6>(stm, wlo0, el); break;
-              case 2: col_issue<NK, 7>(stm, wlo0, el); break;
-              case 3: col_issue<NK, 8>(stm, wlo0, el); break;
-              case 4: col_issue<NK, 9>(stm, wlo0, el); break;
-              case 5: col_issue<NK, 10>(stm, wlo0, el); break;
-              default: col_issue<NK, 11>(stm, wlo0, el); break;
-            }
-            tc::mma_commit_el(&bars[2 + 2 * s], el);
-            par[s] ^= 1u;
-            stage[s] = stage[s] + 1 == COL_NSTAGE ? 0 : stage[s] + 1;
-            --remaining[s];
-            --left;
-          }
-        }
-      }
-    }
-  } else {
+  {
     const int slot = warp / ROW_WARPS, roww = warp % ROW_WARPS;
     RowCtx cx;
     const uint32_t tm = tbase + (uint32_t)slot * 128u + ((uint32_t)(roww * 32) << 16);
@@ -1107,15 +1093,20 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
     cx.a_ready = &bars[1 + 2 * slot];
     cx.acc_ready = &bars[2 + 2 * slot];
     cx.ph = 0;
+    cx.issuer = roww == 0 ? 1 : 0;
+    cx.pha = 0;
+    cx.slot_tm = tbase + (uint32_t)slot * 128u;
+    cx.wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu;
+    cx.el = tc::elect_one();
     cx.gb = 3 * (lane / 3);
     cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
     cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
     for (int tile = blockIdx.x * CSLOT + slot; tile < ntiles; tile += gridDim.x * CSLOT)
-      color_tile(scs, C, src, list2, count, tile, cx, roww, lane, lat_in, out5);
+      color_tile<NK>(scs, C, src, list2, count, tile, cx, roww, lane, lat_in, out5);
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == ISSUER) tc::tmem_dealloc(tbase, 512);
+  if (warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
 }  // namespace
