@@ -8,12 +8,17 @@ and mirrors the argument meaning of the reference's ``KeypointNeRF.query`` /
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
 
 from . import _lib as L
 from .synthetic import layer_table
+
+
+# Host outputs: pinned (fast asynchronous D2H, but a cold pinned allocation costs milliseconds) or pageable.  KPN_PINNED_OUT=0/1.
+_PINNED_OUT = os.environ.get("KPN_PINNED_OUT", "1") != "0"
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -140,8 +145,8 @@ class RayMarcher:
         odev = torch.device("cpu") if host_out else torch.device("cuda", self.device)
 
         def alloc(*shape):
-            if host_out:
-                return torch.empty(*shape, dtype=torch.float32, pin_memory=True)
+            if host_out:   # fresh host tensors per call, like the reference's .cpu() (src/model.py:929)
+                return torch.empty(*shape, dtype=torch.float32, pin_memory=_PINNED_OUT)
             return torch.empty(*shape, dtype=torch.float32, device=odev)
 
         res = {"tex_fg": alloc(3, ny, nx), "depth": alloc(ny, nx), "alpha": alloc(ny, nx)}
