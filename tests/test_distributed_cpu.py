@@ -39,6 +39,17 @@ def _worker(rank, world, port, height, width, q):
     depth = D.gather_rows(band[0], height, rank, world)
     ok = torch.equal(full, _fake_render(0, height, width)) and torch.equal(depth, _fake_render(0, height, width)[0])
     ok = ok and all(float(views[i].mean()) == float(i) for i in range(world))
+
+    class FakeMarcher:   # stands in for RayMarcher.render: the band of a deterministic frame, plus a per-ray debug plane
+        def render(self, *, K, RT, znear, zfar, x0, y0, step, nx, ny, out_device, **kw):
+            assert (x0, step, nx, out_device) == (0, 1, width, "cuda") and kw == {"S_c": 4}
+            f = _fake_render(y0, ny, width)
+            return {"tex_fg": f, "alpha": f[1], "contrib": torch.zeros(ny * nx, 4)}
+
+    sharded = D.render_frame_row_sharded(FakeMarcher(), K=None, RT=None, znear=2.0, zfar=5.0, width=width, height=height, rank=rank,
+                                         world=world, S_c=4)
+    ok = ok and set(sharded) == {"tex_fg", "alpha"} and torch.equal(sharded["tex_fg"], _fake_render(0, height, width))
+    ok = ok and torch.equal(sharded["alpha"], _fake_render(0, height, width)[1])
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
