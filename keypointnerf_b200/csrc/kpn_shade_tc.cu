@@ -988,7 +988,9 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
   constexpr TcPlan plan = make_tc_plan(NK);
   constexpr uint32_t WBYTES = plan.st[GEO_NSTAGE].off;   // per CTA: half of W_hi + half of W_lo of stages 0..5
   constexpr bool PREF = geo_pref(NK);                    // gather staging buffer behind the weights
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  // warp index through a lane-0 broadcast: the compiler then keeps every warp-derived value (slot, lane quarter, column half,
+  // issuer flag, prefetch flags) in uniform registers and branches on them without convergence barriers (-8 % static code)
+  const int t = threadIdx.x, warp = __shfl_sync(FULL, t >> 5, 0), lane = t & 31;
   const uint32_t rank = tc::cluster_ctarank();
   const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int count = *count_ptr;
@@ -1069,7 +1071,7 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
   __shared__ SceneS scs;
   constexpr TcPlan plan = make_tc_plan(NK);
   constexpr uint32_t OFF0 = plan.st[GEO_NSTAGE].off, WBYTES = plan.total_bytes - plan.st[GEO_NSTAGE].off;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int t = threadIdx.x, warp = __shfl_sync(FULL, t >> 5, 0), lane = t & 31;   // warp-uniform (see shade_geo_kernel)
   const int count = *count_ptr;
   const int ntiles = (count + SPT - 1) / SPT;
   stage_scene(scs, *scp, NK, t, TCC_THREADS);
