@@ -62,9 +62,40 @@ def feature_shapes(src_size: int, n_views: int = 3):
     }
 
 
+def silhouette_masks(K: np.ndarray, extrin: np.ndarray, src_size: int, semi_axes=(0.22, 0.64, 0.15)) -> np.ndarray:
+    """Foreground masks (V,1,H,W) bool = silhouettes of an origin-centred ellipsoid seen by each source camera.
+
+    The intersection of the silhouette cones (the visual hull the validity test carves, reference ``src/model.py:729-739``)
+    lies strictly inside the keypoint bounding box, so the LAST sample of every target ray (at the bbox exit, or at zfar for
+    rays that miss the box) is invalid: the reference's final-sample step (``dist[-1] = 1e10``, ``src/model.py:1166``) then
+    multiplies a density of exactly 0 and no ray sits on that discontinuity."""
+    V = K.shape[0]
+    ys, xs = np.meshgrid(np.arange(src_size, dtype=np.float64), np.arange(src_size, dtype=np.float64), indexing="ij")
+    pix = np.stack([xs, ys, np.ones_like(xs)], -1).reshape(-1, 3)
+    inv_ax = 1.0 / np.asarray(semi_axes, dtype=np.float64)
+    out = np.zeros((V, 1, src_size, src_size), dtype=bool)
+    for v in range(V):
+        R = extrin[v, :3, :3].astype(np.float64)
+        t = extrin[v, :3, 3].astype(np.float64)
+        c = -R.T @ t                                             # camera centre
+        d = (pix @ np.linalg.inv(K[v, :3, :3].astype(np.float64)).T) @ R   # world-space pixel rays
+        ds, cs = d * inv_ax, c * inv_ax                          # unit-sphere coordinates
+        a = (ds * ds).sum(-1)
+        b = ds @ cs
+        disc = b * b - a * ((cs * cs).sum() - 1.0)
+        out[v, 0] = (disc >= 0.0).reshape(src_size, src_size)
+    return out
+
+
 def make_scene(src_size: int = 512, n_views: int = 3, n_kpt: int = 18, seed: int = 2,
-               src_azimuths=(0.0, 2.1, 4.2), fg_hole: bool = False) -> dict:
-    """Source-side inputs of the hot path (everything ``query`` reads, reference ``src/model.py:690-782``)."""
+               src_azimuths=(0.0, 2.1, 4.2), fg_hole: bool = False, fg_mode: str | None = None) -> dict:
+    """Source-side inputs of the hot path (everything ``query`` reads, reference ``src/model.py:690-782``).
+
+    ``fg_mode``: "ones" (SURVEY.md section 8d recipe, the bench scene) or "hull" (ellipsoid silhouettes, see
+    ``silhouette_masks``); ``fg_hole`` additionally punches rectangular holes into either."""
+    if fg_mode is None:
+        fg_mode = "ones"
+    assert fg_mode in ("ones", "hull")
     assert len(src_azimuths) >= n_views
     rng_k = np.random.default_rng(1)
     box = np.array([0.6, 1.6, 0.4])
@@ -77,7 +108,10 @@ def make_scene(src_size: int = 512, n_views: int = 3, n_kpt: int = 18, seed: int
     feat8 = rng.standard_normal(sh["feat8"], dtype=F32)
     feat_tex = rng.standard_normal(sh["feat_tex"], dtype=F32)
     img = rng.random(sh["img"], dtype=F32)
-    fg = np.ones(sh["fg"], dtype=bool)
+    K = intrinsic(src_size)
+    extrin = np.stack([look_at_extrinsic(a) for a in src_azimuths[:n_views]], 0)
+    Ks = np.broadcast_to(K, (n_views, 4, 4)).copy()
+    fg = silhouette_masks(Ks, extrin, src_size) if fg_mode == "hull" else np.ones(sh["fg"], dtype=bool)
     if fg_hole:
         # punch rectangular holes so that the foreground-mask term of the validity test
         # (reference src/model.py:737-739) is exercised, including its bilinear edge.
@@ -86,12 +120,9 @@ def make_scene(src_size: int = 512, n_views: int = 3, n_kpt: int = 18, seed: int
             fg[v, 0, a:a + src_size // 8, a:a + src_size // 6] = False
         fg[:, :, : src_size // 10, :] = False
 
-    K = intrinsic(src_size)
-    extrin = np.stack([look_at_extrinsic(a) for a in src_azimuths[:n_views]], 0)
-    Ks = np.broadcast_to(K, (n_views, 4, 4)).copy()
     KRT = np.einsum("vij,vjk->vik", Ks.astype(np.float64), extrin.astype(np.float64)).astype(F32)
     return {
-        "n_views": n_views, "n_kpt": n_kpt, "src_size": src_size,
+        "n_views": n_views, "n_kpt": n_kpt, "src_size": src_size, "fg_mode": fg_mode,
         "kpt3d": kpt3d, "bounds": bounds,
         "feat64": feat64, "feat8": feat8, "feat_tex": feat_tex, "img": img, "fg": fg,
         "K": Ks, "extrin": extrin, "KRT": KRT,
@@ -100,9 +131,10 @@ def make_scene(src_size: int = 512, n_views: int = 3, n_kpt: int = 18, seed: int
     }
 
 
-def make_target(size: int = 512, azimuth: float = 1.0, znear: float = 2.0, zfar: float = 5.0) -> dict:
-    """Target camera dict as ``decode_batch`` builds it (reference ``src/model.py:309-414``)."""
-    K = intrinsic(size)[None]
+def make_target(size: int = 512, azimuth: float = 1.0, znear: float = 2.0, zfar: float = 5.0, zoom: float = 1.0) -> dict:
+    """Target camera dict as ``decode_batch`` builds it (reference ``src/model.py:309-414``); ``zoom`` scales the focal length
+    (small test targets zoom in so that most of their rays cross the visual hull)."""
+    K = intrinsic(size, 550.0 * zoom)[None]
     RT = look_at_extrinsic(azimuth)[None]
     KRT = (K[0].astype(np.float64) @ RT[0].astype(np.float64)).astype(F32)[None]
     return {"K": K, "RT": RT, "KRT": KRT, "width": size, "height": size,

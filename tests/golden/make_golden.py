@@ -2,10 +2,14 @@
 
 Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
-Writes tests/golden/{tiny,tiny_fg,cfg1_tile,cfg3_tile}.npz.  Inputs are regenerated from
-seeds by keypointnerf_b200.synthetic; the .npz files hold the reference's outputs (and,
-for the tiny cases, per-sample intermediates captured with forward hooks), plus an input
-checksum so that drift in the seeded generators is detected.
+Writes tests/golden/<case>.npz for every entry of CASES (or only the cases named on the command
+line).  Inputs are regenerated from seeds by keypointnerf_b200.synthetic; the .npz files hold the
+reference's outputs (and, for the tiny cases, per-sample intermediates captured with forward
+hooks), plus an input checksum so that drift in the seeded generators is detected.
+
+Scenes: "hull" = ellipsoid-silhouette foreground masks (every ray's last sample is invalid, so no
+ray sits on the reference's final-sample discontinuity and every ray is compared); "ones" = the
+SURVEY.md section 8d recipe the bench runs (kept for the config-1/2 passes of the bench scene).
 
 Harness = SURVEY.md Appendix C: stub modules for kornia / pytorch_lightning / skimage /
 imageio, VGGLoss patched out, Tensor.cuda made the identity.
@@ -169,57 +173,66 @@ def run_tile(M, net, scene, target, level, x_off, y_off, S_c, S_f, fine, capture
     return res
 
 
+# name -> dict(src, tgt, az, zoom, level, off, S_c, S_f, fine, n_kpt, seeds, fg_mode, fg_hole, capture, keep)
+def _c(**kw):
+    d = dict(src_size=512, tgt_size=512, azimuth=1.0, zoom=1.0, level=4, x_off=0, y_off=0, S_c=32, S_f=0, fine=False,
+             n_kpt=18, scene_seed=2, w_seed=26, fg_mode="hull", fg_hole=False, capture="none")
+    d.update(kw)
+    return d
+
+
+PI4 = float(np.pi / 4)
+CASES = {
+    # tiny cases: small maps, every per-sample intermediate (capture="all")
+    "tiny": _c(src_size=64, tgt_size=32, zoom=2.0, level=1, S_c=16, S_f=16, fine=True, capture="all"),
+    "tiny_fg": _c(src_size=64, tgt_size=64, zoom=2.0, level=2, x_off=1, y_off=0, S_c=16, S_f=16, fine=True, fg_hole=True,
+                  capture="all"),
+    "tiny_k24": _c(src_size=64, tgt_size=32, zoom=2.0, azimuth=2.5, level=1, S_c=12, S_f=8, fine=True, n_kpt=24,
+                   scene_seed=3, w_seed=5, capture="all"),
+    # BASELINE config 1: one 64x64 strided pass, 32 samples/ray, 512^2 sources (hull scene and the bench scene)
+    "cfg1_tile": _c(),
+    "cfg1_ones": _c(fg_mode="ones", capture="some"),
+    # BASELINE config 2 at config size: one strided pass of the 512x512x128 frame (hull scene and the bench scene)
+    "cfg2_pass": _c(x_off=3, y_off=5, S_c=128, capture="some"),
+    "cfg2_pass_ones": _c(x_off=3, y_off=5, S_c=128, fg_mode="ones", capture="some"),
+    # BASELINE config 3 at config size: 64 coarse + 64 fine
+    "cfg3_pass": _c(x_off=3, y_off=5, S_c=64, S_f=64, fine=True, capture="some"),
+    # BASELINE config 4: 1024^2 target, one level-5 pass (64x64 rays), 128 samples
+    "cfg4_pass": _c(tgt_size=1024, level=5, x_off=7, y_off=9, S_c=128),
+    # BASELINE config 5: second novel view of the sweep (azimuth 1.0 + pi/4)
+    "cfg5_view": _c(azimuth=1.0 + PI4, x_off=2, y_off=6, S_c=128),
+}
+
+
 def main():
     M = import_reference()
     torch.set_num_threads(8)
-    # ---- tiny cases: small maps, all intermediates ------------------------------------------
-    for name, hole in (("tiny", False), ("tiny_fg", True)):
-        scene = syn.make_scene(src_size=64, n_views=3, n_kpt=18, seed=2, fg_hole=hole)
-        weights = syn.make_weights(18, seed=26)
-        target = syn.make_target(size=32, azimuth=1.0)
-        net = build_net(M, 18, weights)
-        res = run_tile(M, net, scene, target, level=2, x_off=1, y_off=0, S_c=16, S_f=16, fine=True, capture=True)
+    names = sys.argv[1:] or list(CASES)
+    nets = {}
+    for name in names:
+        c = CASES[name]
+        scene = syn.make_scene(src_size=c["src_size"], n_views=3, n_kpt=c["n_kpt"], seed=c["scene_seed"],
+                               fg_mode=c["fg_mode"], fg_hole=c["fg_hole"])
+        weights = syn.make_weights(c["n_kpt"], seed=c["w_seed"])
+        target = syn.make_target(size=c["tgt_size"], azimuth=c["azimuth"], zoom=c["zoom"])
+        key = (c["n_kpt"], c["w_seed"])
+        if key not in nets:
+            nets[key] = build_net(M, c["n_kpt"], weights)
+        res = run_tile(M, nets[key], scene, target, level=c["level"], x_off=c["x_off"], y_off=c["y_off"], S_c=c["S_c"],
+                       S_f=c["S_f"], fine=c["fine"], capture=c["capture"] != "none")
+        if c["capture"] == "some":   # outputs + what the compositing / resampling tests need, not the per-sample tensors
+            keys = ["tex_fg", "depth", "alpha", "tex_fg_fine", "depth_fine", "alpha_fine", "sdf", "z_fine", "contrib_coarse",
+                    "z_coarse"]
+            valid_frac = float(res["query_valid"].mean())
+            res = {k: res[k] for k in keys if k in res}
+        else:
+            valid_frac = float(res["query_valid"].mean()) if "query_valid" in res else float("nan")
+        meta = {k: v for k, v in c.items() if k != "capture"}
         res["input_sha256"] = np.frombuffer(checksum(scene, weights).encode(), dtype=np.uint8)
-        res["meta"] = np.frombuffer(json.dumps(dict(src_size=64, tgt_size=32, azimuth=1.0, level=2, x_off=1, y_off=0,
-                                                    S_c=16, S_f=16, fine=True, n_kpt=18, scene_seed=2, w_seed=26,
-                                                    fg_hole=hole)).encode(), dtype=np.uint8)
+        res["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **res)
-        print(name, {k: v.shape for k, v in res.items() if k in ("tex_fg", "tex_fg_fine", "query_out")},
-              "valid frac", float(res["query_valid"].mean()), "alpha mean", float(res["alpha"].mean()))
-    # ---- K=24 tiny case (configs/zju.json default n_kpt) --------------------------------------
-    scene = syn.make_scene(src_size=64, n_views=3, n_kpt=24, seed=3)
-    weights = syn.make_weights(24, seed=5)
-    target = syn.make_target(size=32, azimuth=2.5)
-    net = build_net(M, 24, weights)
-    res = run_tile(M, net, scene, target, level=2, x_off=0, y_off=1, S_c=12, S_f=8, fine=True, capture=True)
-    res["input_sha256"] = np.frombuffer(checksum(scene, weights).encode(), dtype=np.uint8)
-    res["meta"] = np.frombuffer(json.dumps(dict(src_size=64, tgt_size=32, azimuth=2.5, level=2, x_off=0, y_off=1,
-                                                S_c=12, S_f=8, fine=True, n_kpt=24, scene_seed=3, w_seed=5,
-                                                fg_hole=False)).encode(), dtype=np.uint8)
-    np.savez_compressed(os.path.join(HERE, "tiny_k24.npz"), **res)
-    print("tiny_k24 valid frac", float(res["query_valid"].mean()))
-    # ---- BASELINE cfg 1: 64x64 strided pass, 32 samples, src 512^2 ---------------------------
-    scene = syn.make_scene(src_size=512, n_views=3, n_kpt=18, seed=2)
-    weights = syn.make_weights(18, seed=26)
-    target = syn.make_target(size=512, azimuth=1.0)
-    net = build_net(M, 18, weights)
-    res = run_tile(M, net, scene, target, level=4, x_off=0, y_off=0, S_c=32, S_f=0, fine=False)
-    res["input_sha256"] = np.frombuffer(checksum(scene, weights).encode(), dtype=np.uint8)
-    res["meta"] = np.frombuffer(json.dumps(dict(src_size=512, tgt_size=512, azimuth=1.0, level=4, x_off=0, y_off=0,
-                                                S_c=32, S_f=0, fine=False, n_kpt=18, scene_seed=2, w_seed=26,
-                                                fg_hole=False)).encode(), dtype=np.uint8)
-    np.savez_compressed(os.path.join(HERE, "cfg1_tile.npz"), **res)
-    print("cfg1", res["tex_fg"].shape, "alpha mean", float(res["alpha"].mean()))
-    # ---- BASELINE cfg 3 style: hierarchical 24+24 on one pass (kept short for CPU) ----------
-    res = run_tile(M, net, scene, target, level=4, x_off=3, y_off=5, S_c=24, S_f=24, fine=True, capture=True, keep=64)
-    keep = {k: res[k] for k in ("tex_fg", "depth", "alpha", "tex_fg_fine", "depth_fine", "alpha_fine", "sdf",
-                                "z_fine", "contrib_coarse", "z_coarse")}
-    keep["input_sha256"] = np.frombuffer(checksum(scene, weights).encode(), dtype=np.uint8)
-    keep["meta"] = np.frombuffer(json.dumps(dict(src_size=512, tgt_size=512, azimuth=1.0, level=4, x_off=3, y_off=5,
-                                                 S_c=24, S_f=24, fine=True, n_kpt=18, scene_seed=2, w_seed=26,
-                                                 fg_hole=False)).encode(), dtype=np.uint8)
-    np.savez_compressed(os.path.join(HERE, "cfg3_tile.npz"), **keep)
-    print("cfg3", keep["tex_fg_fine"].shape)
+        print(name, res["tex_fg"].shape, "valid frac", valid_frac, "alpha mean", float(res["alpha"].mean()),
+              "alpha max", float(res["alpha"].max()), flush=True)
 
 
 if __name__ == "__main__":

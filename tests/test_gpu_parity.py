@@ -3,15 +3,16 @@ against (a) golden vectors produced by the reference itself and (b) the CPU orac
 seeded inputs.
 
 Gate (BASELINE.json north_star): RGB within 1e-3 abs of the reference, PSNR delta < 0.01 dB.
-  * engine 0 (tcgen05, fp16 operands with two-term weights, fp32 accumulate) is held to exactly that on RGB;
+  * engine 0 (tcgen05, fp16 operands with two-term weights, fp32 accumulate) is held to exactly that on RGB, on EVERY ray;
     accumulated alpha / per-sample compositing weights / depth are looser by the factors below (they are
     not averaged by colours in [0,1] and the density head has a x30 gain in the synthetic recipe);
   * engine 1 (fp32 CUDA cores) is held to fp32 round-off.
-Two documented discontinuities of the reference are handled explicitly rather than by loosening the gate:
-  * the final-sample step (dist[-1] = 1e10): rays whose last-sample density is within rounding noise of 0
-    are excluded from the pointwise comparison (robust_rays) and covered by test_last_sample_step_semantics;
-  * the hierarchical resampling (searchsorted + sort): the free-running fine pass is gated by PSNR and a high
-    quantile; pointwise only with the reference's own z_fine injected (hard parts 3-4).
+Scenes: the goldens use silhouette ("hull") foreground masks, for which the last sample of every ray is invalid, so that no
+ray sits on the reference's final-sample step (dist[-1] = 1e10, src/model.py:1166) and no ray is excluded from any
+comparison.  The bench scene (all-ones masks) does have such rays (0.9 %): its
+config-size passes compare everything in front of the last sample strictly on every ray and the images statistically.
+The hierarchical resampling (searchsorted + sort) is discontinuous: the free-running fine pass is gated by PSNR and a high
+quantile; pointwise only with the reference's own z_fine injected (hard parts 3-4).
 """
 import numpy as np
 import pytest
@@ -26,9 +27,10 @@ pytestmark = pytest.mark.gpu
 
 ENGINES = [0, 1]
 TOL = {
-    0: dict(rgb=1e-3, alpha=3e-3, contrib=3e-3, depth=3e-2, sdf=3e-2, q99_fine=2.5e-3, psnr=55.0),
-    1: dict(rgb=1e-4, alpha=1e-4, contrib=1e-4, depth=2e-3, sdf=2e-3, q99_fine=1e-3, psnr=70.0),
+    0: dict(rgb=1e-3, alpha=3e-3, contrib=3e-3, depth=3e-2, sdf=3e-2, q99_fine=2.5e-3, psnr=70.0),
+    1: dict(rgb=1e-4, alpha=1e-4, contrib=1e-4, depth=2e-3, sdf=2e-3, q99_fine=1e-3, psnr=80.0),
 }
+ALL = np.ones((), dtype=bool)   # every ray
 
 
 def last_sample_rad(scene, weights, target, meta):
@@ -40,14 +42,6 @@ def last_sample_rad(scene, weights, target, meta):
     out, valid = O.query(scene, O.fold_weights(weights), o + d * f_r, d)
     n = meta["tgt_size"] // step
     return out[:, 1].reshape(n, n).numpy(), valid.reshape(n, n).numpy()
-
-
-def robust_rays(scene, weights, target, meta, margin=0.15):
-    """Rays whose FINAL sample is not within `margin` of the density threshold rad == 0 (see module docstring)."""
-    rad, valid = last_sample_rad(scene, weights, target, meta)
-    ok = ~(valid & (np.abs(rad) < margin))
-    assert ok.mean() > 0.97, f"too many fragile rays: {1 - ok.mean():.3f}"
-    return ok
 
 
 def max_err(actual, desired, mask):
@@ -65,7 +59,7 @@ def check(report, what, actual, desired, mask, tol):
 def masked_psnr(a, b, mask):
     e = (np.asarray(a, np.float64) - np.asarray(b, np.float64))[np.broadcast_to(mask, np.shape(a))]
     mse = float(np.mean(e ** 2))
-    return 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
+    return 120.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
 
 
 def _render_tile(net, meta, scene, target, dev="cuda:0", engine=0, fine=None, debug=False, z_override=None):
@@ -120,14 +114,14 @@ def test_tile_coarse_matches_reference(case, engine):
     g, meta, scene, weights, target, net = case
     r = _render_tile(net, meta, scene, target, engine=engine, debug=True)
     t = TOL[engine]
-    ok = robust_rays(scene, weights, target, meta)
+    ok = ALL
     rep = []
     good = check(rep, "tex_fg", r["tex_fg"], g["tex_fg"][0], ok, t["rgb"])
     good &= check(rep, "alpha", r["alpha"], g["alpha"][0], ok, t["alpha"])
-    good &= check(rep, "contrib", r["contrib"], g["contrib_coarse"], ok.reshape(-1, 1), t["contrib"])
+    good &= check(rep, "contrib", r["contrib"], g["contrib_coarse"], ok, t["contrib"])
     good &= check(rep, "depth", r["depth"], g["depth"][0], ok, t["depth"])
     p = masked_psnr(r["tex_fg"], g["tex_fg"][0], ok)
-    print(f"coarse engine {engine}: " + "; ".join(rep) + f"; psnr {p:.1f} dB")
+    print(f"coarse engine {engine}: " + "; ".join(rep) + f"; psnr (all rays) {p:.1f} dB")
     assert good and p > t["psnr"], rep
 
 
@@ -137,7 +131,7 @@ def test_tile_fine_with_reference_depths(case, engine):
     g, meta, scene, weights, target, net = case
     r = _render_tile(net, meta, scene, target, engine=engine, z_override=torch.from_numpy(g["z_fine"]))
     t = TOL[engine]
-    ok = robust_rays(scene, weights, target, meta)
+    ok = ALL
     rep = []
     good = check(rep, "tex_fg_fine", r["tex_fg_fine"], g["tex_fg_fine"][0], ok, t["rgb"])
     good &= check(rep, "alpha_fine", r["alpha_fine"], g["alpha_fine"][0], ok, t["alpha"])
@@ -152,9 +146,9 @@ def test_tile_fine_free_running(case, engine):
     g, meta, scene, weights, target, net = case
     r = _render_tile(net, meta, scene, target, engine=engine, debug=True)
     t = TOL[engine]
-    ok = robust_rays(scene, weights, target, meta)
+    ok = ALL
     dz = np.abs(r["z_fine"] - g["z_fine"])
-    e = np.abs(r["tex_fg_fine"] - g["tex_fg_fine"][0])[np.broadcast_to(ok, (3,) + ok.shape)]
+    e = np.abs(r["tex_fg_fine"] - g["tex_fg_fine"][0]).reshape(-1)
     p = masked_psnr(r["tex_fg_fine"], g["tex_fg_fine"][0], ok)
     print(f"fine free engine {engine}: z q99 {np.quantile(dz, 0.99):.2e} rgb q99 {np.quantile(e, 0.99):.2e} max {e.max():.2e} psnr {p:.1f}")
     assert np.quantile(dz, 0.99) < 1e-3
@@ -162,51 +156,78 @@ def test_tile_fine_free_running(case, engine):
     assert np.quantile(e, 0.99) < t["q99_fine"]
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-def test_cfg1_tile_matches_reference(engine):
-    """BASELINE config 1 (64x64 strided pass, 32 samples, 512^2 sources) against the reference's output."""
-    g, meta, sha = load_golden("cfg1_tile")
+def _golden_case(name):
+    g, meta, sha = load_golden(name)
     scene, weights, target = scene_from_meta(meta)
     assert checksum(scene, weights) == sha
-    net = build_model(weights, meta["n_kpt"], "cuda:0")
-    r = _render_tile(net, meta, scene, target, engine=engine)
+    return g, meta, scene, weights, target, build_model(weights, meta["n_kpt"], "cuda:0")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["cfg1_tile", "cfg2_pass", "cfg4_pass", "cfg5_view"])
+def test_config_size_pass_matches_reference(name, engine):
+    """One strided pass of BASELINE configs 1 (32 samples), 2 (512^2 x 128), 4 (1024^2 target, level 5) and 5 (second view of
+    the sweep) at config size against the reference's own output of that pass; every ray is compared."""
+    g, meta, scene, weights, target, net = _golden_case(name)
+    r = _render_tile(net, meta, scene, target, engine=engine, debug="contrib_coarse" in g)
     t = TOL[engine]
-    ok = robust_rays(scene, weights, target, meta)
     rep = []
-    good = check(rep, "tex_fg", r["tex_fg"], g["tex_fg"][0], ok, t["rgb"])
-    good &= check(rep, "alpha", r["alpha"], g["alpha"][0], ok, t["alpha"])
-    p = masked_psnr(r["tex_fg"], g["tex_fg"][0], ok)
-    p_all = psnr(r["tex_fg"], g["tex_fg"][0])
-    print(f"cfg1 engine {engine}: " + "; ".join(rep) + f"; psnr robust {p:.1f} dB, all rays {p_all:.1f} dB, robust frac {ok.mean():.4f}")
+    good = check(rep, "tex_fg", r["tex_fg"], g["tex_fg"][0], ALL, t["rgb"])
+    good &= check(rep, "alpha", r["alpha"], g["alpha"][0], ALL, t["alpha"])
+    good &= check(rep, "depth", r["depth"], g["depth"][0], ALL, t["depth"])
+    if "contrib_coarse" in g:
+        good &= check(rep, "contrib", r["contrib"], g["contrib_coarse"], ALL, t["contrib"])
+    p = psnr(r["tex_fg"], g["tex_fg"][0])
+    print(f"{name} engine {engine}: " + "; ".join(rep) + f"; psnr (all rays) {p:.1f} dB")
     assert good and p > t["psnr"], rep
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-def test_cfg3_tile_matches_reference(engine):
-    """BASELINE config 3 style (hierarchical) on one pass."""
-    g, meta, sha = load_golden("cfg3_tile")
-    scene, weights, target = scene_from_meta(meta)
-    net = build_model(weights, meta["n_kpt"], "cuda:0")
+def test_cfg3_pass_matches_reference(engine):
+    """BASELINE config 3 at config size (64 coarse + 64 fine samples) on one pass: coarse image and compositing weights,
+    the fine image on the reference's own resampled depths (pointwise) and free-running (PSNR + resampled-depth quantile)."""
+    g, meta, scene, weights, target, net = _golden_case("cfg3_pass")
     r = _render_tile(net, meta, scene, target, engine=engine, debug=True)
     t = TOL[engine]
-    ok = robust_rays(scene, weights, target, meta)
     rep = []
-    good = check(rep, "tex_fg", r["tex_fg"], g["tex_fg"][0], ok, t["rgb"])
-    good &= check(rep, "contrib", r["contrib"], g["contrib_coarse"], ok.reshape(-1, 1), t["contrib"])
-    p_free = masked_psnr(r["tex_fg_fine"], g["tex_fg_fine"][0], ok)
+    good = check(rep, "tex_fg", r["tex_fg"], g["tex_fg"][0], ALL, t["rgb"])
+    good &= check(rep, "contrib", r["contrib"], g["contrib_coarse"], ALL, t["contrib"])
+    p_free = psnr(r["tex_fg_fine"], g["tex_fg_fine"][0])
+    dz = np.abs(r["z_fine"] - g["z_fine"])
     r2 = _render_tile(net, meta, scene, target, engine=engine, z_override=torch.from_numpy(g["z_fine"]))
-    good &= check(rep, "tex_fg_fine@ref-z", r2["tex_fg_fine"], g["tex_fg_fine"][0], ok, t["rgb"])
-    good &= check(rep, "alpha_fine@ref-z", r2["alpha_fine"], g["alpha_fine"][0], ok, t["alpha"])
-    print(f"cfg3 engine {engine}: " + "; ".join(rep) + f"; free-running fine psnr {p_free:.1f} dB")
-    assert good and p_free > 50.0, rep
+    good &= check(rep, "tex_fg_fine@ref-z", r2["tex_fg_fine"], g["tex_fg_fine"][0], ALL, t["rgb"])
+    good &= check(rep, "alpha_fine@ref-z", r2["alpha_fine"], g["alpha_fine"][0], ALL, t["alpha"])
+    good &= check(rep, "sdf@ref-z", r2["sdf"], g["sdf"][0], ALL, t["sdf"])
+    p_ref = psnr(r2["tex_fg_fine"], g["tex_fg_fine"][0])
+    print(f"cfg3 engine {engine}: " + "; ".join(rep) + f"; fine psnr @ref-z {p_ref:.1f} dB, free-running {p_free:.1f} dB, "
+          f"z_fine q99 {np.quantile(dz, 0.99):.2e}")
+    assert good and p_ref > t["psnr"] and p_free > 55.0 and np.quantile(dz, 0.99) < 1e-3, rep
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["cfg1_ones", "cfg2_pass_ones"])
+def test_bench_scene_pass_matches_reference(name, engine):
+    """The bench scene (all-ones foreground masks, 46 % of the samples valid) at config size.  About 1 % of its rays end on a
+    valid sample whose density is within rounding of 0, which the reference's dist[-1] = 1e10 turns into alpha 0 or 1; so the
+    compositing weights of every sample IN FRONT of the last one are compared strictly on every ray, and the image by the
+    fraction of rays beyond the gate and by the PSNR over all rays."""
+    g, meta, scene, weights, target, net = _golden_case(name)
+    r = _render_tile(net, meta, scene, target, engine=engine, debug=True)
+    t = TOL[engine]
+    rep = []
+    good = check(rep, "contrib[:, :-1]", r["contrib"][:, :-1], g["contrib_coarse"][:, :-1], ALL, t["contrib"])
+    e = np.abs(r["tex_fg"] - g["tex_fg"][0]).max(0)
+    frac = float((e > t["rgb"]).mean())
+    p = psnr(r["tex_fg"], g["tex_fg"][0])
+    print(f"{name} engine {engine}: " + "; ".join(rep) + f"; rays beyond the rgb gate {frac:.4%} (final-sample step); "
+          f"rgb q99 {np.quantile(e, 0.99):.2e}; psnr (all rays) {p:.1f} dB")
+    assert good and frac < 0.015 and np.quantile(e, 0.98) < t["rgb"] and p > 40.0, rep
 
 
 def test_last_sample_step_semantics():
-    """The reference's step at the final sample (dist[-1] = 1e10) is reproduced: on rays whose last-sample density
-    is clearly positive the accumulated alpha is 1, for the reference and for both engines."""
-    g, meta, sha = load_golden("cfg1_tile")
-    scene, weights, target = scene_from_meta(meta)
-    net = build_model(weights, meta["n_kpt"], "cuda:0")
+    """The reference's step at the final sample (dist[-1] = 1e10) is reproduced: on rays of the bench scene whose last-sample
+    density is clearly positive the accumulated alpha is 1, for the reference and for both engines."""
+    g, meta, scene, weights, target, net = _golden_case("cfg1_ones")
     rad, valid = last_sample_rad(scene, weights, target, meta)
     opaque = valid & (rad > 0.15)
     assert opaque.sum() > 100

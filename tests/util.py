@@ -20,9 +20,9 @@ def load_golden(name):
 
 def scene_from_meta(meta):
     scene = syn.make_scene(src_size=meta["src_size"], n_views=3, n_kpt=meta["n_kpt"], seed=meta["scene_seed"],
-                           fg_hole=meta["fg_hole"])
+                           fg_hole=meta["fg_hole"], fg_mode=meta.get("fg_mode", "ones"))
     weights = syn.make_weights(meta["n_kpt"], seed=meta["w_seed"])
-    target = syn.make_target(size=meta["tgt_size"], azimuth=meta["azimuth"])
+    target = syn.make_target(size=meta["tgt_size"], azimuth=meta["azimuth"], zoom=meta.get("zoom", 1.0))
     return scene, weights, target
 
 
