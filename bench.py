@@ -2,21 +2,27 @@
 """Benchmark of the ray-march hot path (BASELINE.json metric: rays/sec, 512x512, 128 samples/ray,
 3 source views, 18 keypoints).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config {2,3,4,5}] [--scene {ones,hull}] [--impl reference]
 
 A step = one pass of the hot path over one synthetic frame: re-layout of the (new) source feature
-maps + ray generation + sampling + shading + compositing for every pixel of a 512x512 novel view.
-With N > 1 (torchrun) each rank renders its own novel view of the same scene (BASELINE config 5,
-weak scaling) and the frames are exchanged with ONE NCCL all-gather.
+maps + ray generation + sampling + shading + compositing for every pixel of the novel view.
+
+BASELINE.json configs (config 1 is the reference's CPU-runnable plumbing case: a parity test, not a bench line):
+  2 (default, the headline)  512x512, 128 samples/ray.  N > 1 ranks: one novel view per rank (= config 5, weak scaling).
+  3                          512x512, 64 coarse + 64 fine samples, early-ray termination at 1e-4; ranks as in 2.
+  4                          ONE 1024x1024 frame, 128 samples/ray, split into lattice phases over the N ranks (strong scaling).
+  5                          alias of 2 (the render_dynamic.py-style sweep: one 512x512 view per GPU).
+The frames are exchanged with ONE NCCL all-gather.
 
 `value`   : inputs resident in HBM, CUDA-event time on the launch stream, max over ranks.
 `e2e`     : the same metric through the reference-facing API (`KeypointNeRF.render_pifu_nerf`) with
             pinned HOST tensors in and host tensors out (H2D + D2H inside the timed region).
-`roofline`: dominant (shading) kernel, algorithmic FLOPs of the samples it shades / its device time
-            measured live with CUDA events inside the timed region, against the measured dense
-            bf16 tensor peak in MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the CPU oracle port (oracle/, torch-CPU, all host threads) on a
-            bounded sample of the same workload (one 64x64 strided pass = 4096 rays x 128 samples).
+`roofline`: the dominant kernel (shade_geo_kernel): algorithmic FLOPs of the samples it shaded / its device time, both
+            measured live (valid-sample counter of the launch, CUDA events around the kernel on the launch stream inside the
+            timed region), against the measured dense bf16 tensor peak in MEASURED_PEAKS.json; `pair` adds the colour kernel
+            (executed FLOPs: 419 200 per valid sample + 79 536 per sample with density > 0).
+`cpu_baseline` / `--impl reference`: the CPU oracle port (oracle/, torch-CPU, all host threads) on a bounded sample of the
+            same workload (a strided pass of the same frame: 4096 rays, fewer when that would take too long).
 """
 from __future__ import annotations
 
@@ -33,32 +39,41 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SIZE = 512
-S_C = 128
 N_KPT = 18
 N_VIEWS = 3
-WORKLOAD = "512x512 frame, 128 samples/ray (fine off), 3 source views 512^2, 18 keypoints, random maps+weights"
+CONFIGS = {
+    2: dict(size=512, S_c=128, S_f=0, fine=False, ert=0.0, part="views",
+            workload="512x512 frame, 128 samples/ray (fine off), 3 source views 512^2, 18 keypoints, random maps+weights"),
+    3: dict(size=512, S_c=64, S_f=64, fine=True, ert=1e-4, part="views",
+            workload="512x512 frame, 64 coarse + 64 fine samples/ray, early-ray termination 1e-4, 3 source views 512^2, "
+                     "18 keypoints, random maps+weights"),
+    4: dict(size=1024, S_c=128, S_f=0, fine=False, ert=0.0, part="lattice",
+            workload="1024x1024 frame, 128 samples/ray (fine off), 3 source views 512^2, 18 keypoints, random maps+weights"),
+}
+CONFIGS[5] = CONFIGS[2]
 
 
-def flop_per_sample(n_kpt: int, n_views: int) -> int:
-    """Dense-layer FLOPs (2*MAC) per evaluated sample, SURVEY.md section 8a."""
+def flops(n_kpt: int, n_views: int):
+    """Dense-layer FLOPs (2*MAC), SURVEY.md section 8a: (per valid sample: geometry MLP of every view + pooled density tail +
+    compress layer, per sample with density > 0: the IBR colour head of every view)."""
     enc = 7 * n_kpt
     geo = (enc + 64) * 128 + 128 * 128 + 136 * 120 + 120 * 64
     ibr = 4 * 16 + 16 * 35 + 105 * 64 + 64 * 32 + 32 * 32 + 32 * 33 + 32 * 32 + 32 + 37 * 16 + 16 * 8 + 8
     pooled = 128 * 64 + 64 * 64 + 64 * 2 + 128 * 24
-    return 2 * (n_views * (geo + ibr) + pooled)
+    return 2 * (n_views * geo + pooled), 2 * n_views * ibr
 
 
 def ncu_traffic():
-    """DRAM bytes per shading launch pair (geometry + colour kernel) from the latest committed ncu capture (profiles/*_traffic.json,
-    written by tools/summarize_profile.py); None when no capture is committed."""
+    """DRAM bytes per launch of the shading kernels from the latest committed ncu capture (profiles/*_traffic.json, written
+    by tools/summarize_profile.py); None when no capture is committed."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
     if not files:
-        return None, None
+        return None, None, None
     d = json.load(open(files[-1]))
-    tot = sum(k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0) for k in d["kernels"].values())
-    return tot, os.path.basename(files[-1])
+    per = {k: v.get("dram__bytes_read.sum", 0.0) + v.get("dram__bytes_write.sum", 0.0) for k, v in d["kernels"].items()}
+    geo = next((v for k, v in per.items() if "geo" in k), None)
+    return geo, sum(per.values()), os.path.basename(files[-1])
 
 
 def peaks():
@@ -119,55 +134,60 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_rays_per_s(steps: int, warmup: int, threads: int | None = None):
-    """Oracle port on the host cores: one 64x64 strided pass (4096 rays x 128 samples) per step.  The torch-CPU path is bound by
-    materialised intermediates and does not scale to every core of a large host, so (unless `threads` is given) the first two
-    untimed passes try all cores and 16 threads and the timed passes use the faster setting; `cores` reports the threads used."""
+def cpu_port_rays_per_s(cfg: dict, scene_kind: str, steps: int, warmup: int, budget_s: float = 150.0):
+    """Oracle port on ALL host cores (set explicitly: under torchrun OMP_NUM_THREADS is 1).  One step = the first `rays` pixels of
+    a 64x64 strided pass of the configured frame; `rays` starts at 4096 (a full pass) and is cut (to a multiple of 64, at least
+    256) when the first untimed pass says `steps` passes would exceed `budget_s`, so that the run ends within a few minutes
+    whatever --steps the caller asks for.  The torch-CPU path is bound by materialised intermediates and may run faster on 16
+    threads than on every core of a large host: the first two untimed passes try both and the timed ones use the faster."""
     import torch
     from keypointnerf_b200 import synthetic as syn
     from oracle import kpnerf_oracle as O
-    scene = syn.make_scene(SIZE, N_VIEWS, N_KPT)
+    scene = syn.make_scene(512, N_VIEWS, N_KPT, fg_mode=scene_kind)
     fw = O.fold_weights(syn.make_weights(N_KPT))
-    target = syn.make_target(SIZE, azimuth=1.0)
+    target = syn.make_target(cfg["size"], azimuth=1.0)
+    step = cfg["size"] // 64
 
-    def one_pass(i):
+    def one_pass(i, rays):
+        pix = O.pixel_lattice(cfg["size"], cfg["size"], step, i % step, (i // step) % step)[:rays]
         t0 = time.perf_counter()
-        O.render_tile(scene, fw, target, 4, i % 8, (i // 8) % 8, S_C)
+        O.render_pixels(scene, fw, target, pix, cfg["S_c"], cfg["S_f"], cfg["fine"])
         return time.perf_counter() - t0
 
     with torch.no_grad():
-        if threads:
-            torch.set_num_threads(threads)
-        else:
-            all_cores = torch.get_num_threads()
-            cands = sorted({all_cores, min(16, all_cores)}, reverse=True)
-            if len(cands) > 1:
-                one_pass(0)                      # first call of the process: allocator / thread-pool warm-up, not a measurement
-                probe = {}
-                for n in cands:
-                    torch.set_num_threads(n)
-                    probe[n] = one_pass(1)
-                torch.set_num_threads(min(probe, key=probe.get))
+        all_cores = os.cpu_count() or 1
+        torch.set_num_threads(all_cores)
+        rays = 4096
+        one_pass(0, 256)                         # first call of the process: allocator / thread-pool warm-up, not a measurement
+        probe = {}
+        for n in sorted({all_cores, min(16, all_cores)}, reverse=True):
+            torch.set_num_threads(n)
+            probe[n] = one_pass(1, 1024)
+        torch.set_num_threads(min(probe, key=probe.get))
         cores = torch.get_num_threads()
+        est = min(probe.values()) * 4.0 * (steps + warmup)
+        if est > budget_s:
+            rays = max(256, int(4096 * budget_s / est) // 64 * 64)
         times = []
         for i in range(warmup + steps):
-            dt = one_pass(i)
+            dt = one_pass(i, rays)
             if i >= warmup:
                 times.append(dt)
-    rays = 64 * 64
-    return rays * len(times) / sum(times), cores, sum(times) / len(times) * 1e3
+    return rays * len(times) / sum(times), cores, sum(times) / len(times) * 1e3, rays
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    val, cores, ms = cpu_port_rays_per_s(args.steps, args.warmup)
-    sample = "one 64x64 strided pass of the 512x512 frame per step (4096 rays x 128 samples)"
+    val, cores, ms, rays = cpu_port_rays_per_s(cfg, args.scene, args.steps, args.warmup)
+    sample = (f"the first {rays} rays of a 64x64 strided pass of the frame per step ({rays} rays x {cfg['S_c'] + cfg['S_f']} "
+              f"samples), {cores} threads")
     line = {"impl": "reference", "metric": "rays/sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if cfg["part"] == "lattice" else "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference PyTorch path (the reference is "
+            "config": {"workload": cfg["workload"], "note": "CPU oracle port of the reference PyTorch path (the reference is "
                        "Python and cannot travel to the GPU box); bounded sample per step"},
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -182,12 +202,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--scene", default="ones", choices=["ones", "hull"],
+                    help="ones: SURVEY.md 8d recipe (all-foreground masks, ~46 %% of the samples valid); hull: silhouette masks "
+                         "(~1.6 %% valid, like real captures)")
     ap.add_argument("--engine", type=int, default=0)
+    ap.add_argument("--n-kpt", type=int, default=N_KPT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, cfg)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -205,16 +231,25 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    size, S_c, S_f, fine, ert = cfg["size"], cfg["S_c"], cfg["S_f"], cfg["fine"], cfg["ert"]
+    lattice = cfg["part"] == "lattice"
+    n_kpt = args.n_kpt
 
-    scene = syn.make_scene(SIZE, N_VIEWS, N_KPT)
-    weights = syn.make_weights(N_KPT)
-    target = syn.make_target(SIZE, azimuth=1.0 + rank * np.pi / 4.0)   # one novel view per rank
-    net = build_model(weights, N_KPT, dev)
+    scene = syn.make_scene(512, N_VIEWS, n_kpt, fg_mode=args.scene)
+    weights = syn.make_weights(n_kpt)
+    # config 4: every rank renders its lattice phase of the SAME view; otherwise one novel view per rank
+    target = syn.make_target(size, azimuth=1.0 if lattice else 1.0 + rank * np.pi / 4.0)
+    net = build_model(weights, n_kpt, dev)
     net.engine = args.engine
     a = scene_tensors(scene, target, dev)
     h = scene_tensors(scene, target, "cpu", pin=True)
     m = net.marcher()
+    m.reserve(size * size // (world if lattice else 1), S_c + S_f)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    kw = dict(S_c=S_c, S_f=S_f, fine=fine, engine=args.engine, ert_eps=ert)
+    key = "tex_fg_fine" if fine else "tex_fg"
+    gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    gstate = {"k": -1}
 
     def bind(t):
         m.set_scene(KRT=t["cam"]["KRT"], extrin=t["sp_data"]["extrin"], kpt3d=t["sp_data"]["kpt3d"].reshape(-1, 3),
@@ -224,18 +259,32 @@ def main():
 
     def step_device():
         bind(a)   # every step is a new frame: the atlases are re-packed
-        res = m.render(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=target["znear"], zfar=target["zfar"],
-                       x0=0, y0=0, step=1, nx=SIZE, ny=SIZE, S_c=S_C, fine=False, out_device="cuda", engine=args.engine)
-        frames = D.gather_views(res["tex_fg"], world)
-        return frames
+        k = gstate["k"]
+        if lattice:
+            y0, x0, sy, sx = D.lattice_phase(rank, world)
+            res = m.render(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=target["znear"], zfar=target["zfar"], x0=x0, y0=y0,
+                           step=sx, step_y=sy, nx=size // sx, ny=size // sy, out_device="cuda", **kw)
+            if k >= 0:
+                gev[k][0].record()
+            out = D.gather_lattice(res[key], world)
+        else:
+            res = m.render(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=target["znear"], zfar=target["zfar"],
+                           x0=0, y0=0, step=1, nx=size, ny=size, out_device="cuda", **kw)
+            if k >= 0:
+                gev[k][0].record()
+            out = D.gather_views(res[key], world)
+        if k >= 0:
+            gev[k][1].record()
+        return out
 
-    cfgk = dict(sample_per_ray_c=S_C, sample_per_ray_f=0, fine=False, uniform=True)
+    cfgk = dict(sample_per_ray_c=S_c, sample_per_ray_f=S_f, fine=fine, uniform=True, ert_eps=ert)
+    level = int(np.log2(size)) - 5   # render_novel_views: max(0, log2(im_h) - 5), reference src/model.py:485
 
     def step_e2e():
         net._scene_key = None   # new frame: host feature maps are uploaded again
-        return net.render_pifu_nerf(net, h["img"], h["cam"], h["cam_tar"], level=4, sp_data=h["sp_data"],
+        return net.render_pifu_nerf(net, h["img"], h["cam"], h["cam_tar"], level=level, sp_data=h["sp_data"],
                                     feat_geo=h["feat_geo"], feat_tex=h["feat_tex"], src_foreground_mask=h["fg"],
-                                    bounds=h["bounds"], mask_at_box=None, **cfgk)
+                                    bounds=h["bounds"], mask_at_box=None, dist_shard=(rank, world) if lattice else None, **cfgk)
 
     def barrier():
         if world > 1:
@@ -255,20 +304,23 @@ def main():
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (not timed)
+        gstate["k"] = k
         evs[k][0].record()
         step_device()
         evs[k][1].record()
+    gstate["k"] = -1
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    st = m.stats()
+    st = m.stats()   # counters of the LAST step's render, event times summed over the timed steps
     m.set_profiling(False)
-    ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_total = float(tms.item())
-    rays_per_step = SIZE * SIZE * world
+    ms_rank = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    gather_ms = sum(e0.elapsed_time(e1) for e0, e1 in gev)
+    mine = torch.tensor([ms_rank, st["shade_ms"], st["geo_ms"], gather_ms, float(st["samples_valid"]), float(st["samples_coloured"])],
+                        dtype=torch.float64, device=dev)
+    per_rank = D.gather_views(mine, world).cpu().numpy()
+    ms_total = float(per_rank[:, 0].max())
+    rays_per_step = size * size * (1 if lattice else world)
     value = rays_per_step * args.steps / (ms_total * 1e-3)
     launches = st["kernel_launches"] - launches0
 
@@ -293,40 +345,54 @@ def main():
                h["sp_data"]["kpt3d"], h["bounds"], h["cam_tar"]["K"], h["cam_tar"]["RT"]])
     d2h = sum(int(v.numel() * v.element_size()) for v in out.values())
 
-    fps = flop_per_sample(N_KPT, N_VIEWS)
+    f_geo, f_ibr = flops(n_kpt, N_VIEWS)
     pk = peaks()
-    valid_per_step = st["samples_valid"]
-    shade_ms = st["shade_ms"]
-    ach = (fps * valid_per_step * args.steps) / (shade_ms * 1e-3) / 1e12 if shade_ms > 0 else None
-    traffic, traffic_src = ncu_traffic()
-    roofline = {"bound": "tensor", "kernel": "shade_geo_kernel + shade_color_kernel (per-sample gather+encode+MLPs; geometry is ~85% of it)",
-                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": (ach / pk["tflops"]) if ach else None,
-                "traffic": traffic, "traffic_unit": "DRAM bytes per launch pair (one chunk = one 512x512x128 frame), ncu --set full",
-                "traffic_source": traffic_src,
-                "peak_source": pk["source"], "flop_per_sample": fps, "valid_samples_per_step": valid_per_step,
-                "valid_frac": valid_per_step / float(SIZE * SIZE * S_C), "shade_ms_per_step": shade_ms / args.steps,
+    n_eval = size * size * (S_c + (S_c + S_f if fine else 0)) // (world if lattice else 1)   # samples evaluated per rank and step
+    valid, coloured = st["samples_valid"], st["samples_coloured"]
+    geo_ms, shade_ms = st["geo_ms"], st["shade_ms"]
+    ach_geo = f_geo * valid * args.steps / (geo_ms * 1e-3) / 1e12 if geo_ms > 0 else None
+    ach_pair = (f_geo * valid + f_ibr * coloured) * args.steps / (shade_ms * 1e-3) / 1e12 if shade_ms > 0 else None
+    t_geo, t_pair, t_src = ncu_traffic()
+    roofline = {"bound": "tensor", "kernel": "shade_geo_kernel (gather + keypoint encoding + geometry MLP + pooling + density tail)",
+                "achieved": ach_geo, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": (ach_geo / pk["tflops"]) if ach_geo else None,
+                "traffic": t_geo, "traffic_unit": "DRAM bytes per launch (one chunk = one 512x512x128 frame), ncu --set full",
+                "traffic_source": t_src, "peak_source": pk["source"],
+                "flop_per_valid_sample": f_geo, "flop_per_coloured_sample": f_ibr,
+                "valid_samples_per_step": valid, "coloured_samples_per_step": coloured,
+                "valid_frac": valid / float(n_eval), "geo_ms_per_step": geo_ms / args.steps,
+                "pair": {"kernels": "shade_geo_kernel + shade_color_kernel", "achieved": ach_pair,
+                         "frac": (ach_pair / pk["tflops"]) if ach_pair else None, "ms_per_step": shade_ms / args.steps,
+                         "traffic": t_pair},
                 "shade_launches_per_step": st["shade_launches"] / args.steps,
-                "shade_share_of_step": (shade_ms / ms_total) if ms_total else None,
-                "nominal_tflops_all_samples": fps * SIZE * SIZE * S_C * args.steps / (ms_total * 1e-3) / 1e12}
+                "shade_share_of_step": (shade_ms / ms_rank) if ms_rank else None,
+                "nominal_tflops_all_samples": (f_geo + f_ibr) * n_eval * args.steps / (ms_rank * 1e-3) / 1e12}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, cores, ms = cpu_port_rays_per_s(args.cpu_steps, 1)
+        val, cores, ms, rays = cpu_port_rays_per_s(cfg, args.scene, args.cpu_steps, 1)
         cpu = {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_steps} x one 64x64 strided pass of the same frame (4096 rays x 128 samples), "
-                         f"{ms:.0f} ms each, torch-CPU oracle port"}
+               "sample": f"{args.cpu_steps} x the first {rays} rays of a 64x64 strided pass of the same frame ({rays} rays x "
+                         f"{S_c + S_f} samples), {ms:.0f} ms each, torch-CPU oracle port"}
 
     if rank == 0:
+        part = (f"one {size}x{size} frame in {world} lattice phases (one per GPU), one all-gather of the phases" if lattice else
+                f"one novel view per GPU x{world}, one all-gather of frames")
+        names = ["ms", "shade_ms", "geo_ms", "all_gather_ms", "valid_samples", "coloured_samples"]
         line = {"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "strong" if lattice else "weak",
                 "vs_baseline": None, "dtype": "fp32" if args.engine == 1 else net.marcher_dtype(), "data": "synthetic",
-                "config": {"workload": WORKLOAD, "parallelism": f"one novel view per GPU x{world}, one all-gather of frames",
+                "config": {"workload": cfg["workload"], "baseline_config": args.config, "parallelism": part,
+                           "scene": f"{args.scene} foreground masks", "n_kpt": n_kpt,
                            "l2": "flushed between timed iterations (256 MiB write)", "engine": args.engine,
                            "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_each": [round(x, 2) for x in e2e_each]},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": launches, "roofline": roofline,
+                "per_rank": [{n: (float(v) / args.steps if n.endswith("ms") else float(v)) for n, v in zip(names, row)}
+                             for row in per_rank],
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

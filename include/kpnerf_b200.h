@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KPN_ABI_VERSION 1
+#define KPN_ABI_VERSION 2
 #define KPN_MAX_VIEWS 4
 #define KPN_MAX_KPT 32
 #define KPN_NUM_LAYERS 19
@@ -88,18 +88,28 @@ typedef struct {
   const float* img;     int img_h, img_w;            /* img_in (V,3,H,W) */
   const uint8_t* fg;    int fg_h, fg_w;              /* src_foreground_mask (V,1,H,W) bool; NULL = disable_fg_mask */
   int mem;                                           /* kpn_mem of ALL pointers above */
+  int layout;                                        /* bit mask of KPN_NHWC_*: that map is already stored [V][H][W][C]
+                                                        (what the channels-last encoders emit): no re-layout pass; a DEVICE
+                                                        map is then gathered from IN PLACE and must stay alive and unchanged
+                                                        until the next kpn_set_scene */
 } kpn_scene;
+#define KPN_NHWC_FEAT64 1
+#define KPN_NHWC_FEAT8 2
+#define KPN_NHWC_FEATTEX 4
 
 /* Target camera + pixel lattice (reference src/model.py:973-976,1018-1036).
- * Pixel (i,j), 0<=i<nx, 0<=j<ny is x = x0 + step*i, y = y0 + step*j; outputs are indexed [j*nx+i].
- * The reference's strided pass (level, stride=[x_off,y_off]) is step=2^(level-1), x0=x_off, y0=y_off,
- * nx=width/step, ny=height/step; a full frame is step=1, nx=width, ny=height. */
+ * Pixel (i,j), 0<=i<nx, 0<=j<ny is x = x0 + step*i, y = y0 + step_y*j; outputs are indexed [j*nx+i].
+ * The reference's strided pass (level, stride=[x_off,y_off]) is step=step_y=2^(level-1), x0=x_off, y0=y_off,
+ * nx=width/step, ny=height/step; a full frame is step=1, nx=width, ny=height.  step_y = 0 means step_y = step; a
+ * different step_y gives the rectangular lattice phases of the multi-GPU frame partition (one phase per rank: every
+ * phase sees the whole image, so the ranks are load-balanced by construction; reference src/model.py:916-923). */
 typedef struct {
   const float* K;    /* (4,4) cam_tar["K"][0] */
   const float* RT;   /* (4,4) cam_tar["RT"][0] */
   float znear, zfar;
   int x0, y0, step, nx, ny;
   int mem;           /* kpn_mem of K, RT */
+  int step_y;        /* 0: same as step */
 } kpn_target;
 
 typedef struct {
@@ -109,8 +119,9 @@ typedef struct {
   float ert_eps;          /* early-ray-termination transmittance threshold; 0 = off (reference behaviour) */
   const float* z_fine_override; /* optional (R, S_c+S_f) sorted depths replacing the resampled ones (test hook; same kpn_mem as kpn_out) */
   int engine;             /* 0 = default: tcgen05, fp16 operands with two-term (hi+lo) weights, fp32 accumulate;
-                             1 = fp32 CUDA-core engine (parity anchor; also used for shapes the tensor-core engine
-                                 does not cover: n_views != 3, n_kpt not in {18,24}, sp_level != 3);
+                             1 = fp32 CUDA-core engine (parity anchor, ~25x slower; the ONLY engine for shapes the tensor-core
+                                 engine does not cover: n_views != 3, n_kpt not in {18,24}, sp_level != 3 -- such shapes
+                                 fail with KPN_ERR_UNSUPPORTED unless engine = 1 is requested explicitly);
                              2 = tcgen05 with single-term fp16 weights (faster issue, ~2x the rounding error) */
 } kpn_opts;
 
@@ -134,6 +145,8 @@ typedef struct {
   uint64_t kernel_launches; /* kernels launched by this context since creation */
   uint64_t shade_launches;  /* launches of the dominant (shading) kernel timed since the last kpn_get_stats */
   double shade_ms;          /* their summed device time (CUDA events on the launch stream); 0 unless profiling */
+  uint64_t samples_coloured;/* valid samples with density > 0, i.e. shaded by the colour kernel too (tensor-core engine) */
+  double geo_ms;            /* the geometry kernel's part of shade_ms (tensor-core engine, profiling on) */
 } kpn_stats;
 
 int kpn_abi_version(void);
@@ -165,6 +178,18 @@ int kpn_query(kpn_ctx* ctx, const float* pts, const float* view, int n, float* o
 /* Counters of the last call (+ the shading-kernel timings accumulated since the previous
  * kpn_get_stats when profiling is on).  Synchronises `stream` (debug/bench only). */
 int kpn_get_stats(kpn_ctx* ctx, kpn_stats* stats, void* stream);
+
+/* Non-blocking health check.  Every render/query enqueues a copy of the tensor-core kernels' device watchdog words into
+ * pinned host memory; this call (and the start of every other call) looks at the last copy that has landed.  If a barrier
+ * wait gave up (a protocol bug: the affected launch and every later tensor-core launch produced garbage) it returns
+ * KPN_ERR_CUDA with the location in kpn_last_error, clears the device flag (re-arming the engine) and the host copy.
+ * Callers that synchronise the stream anyway (host outputs) call it right after: RayMarcher.render does. */
+int kpn_check_health(kpn_ctx* ctx, void* stream);
+
+/* Pre-sizes every workspace buffer for renders of up to max_rays rays x max_samples samples per ray (coarse + fine), so that
+ * later kpn_render calls of at most that size never allocate or free device memory.  Without it buffers grow on demand
+ * (cudaFree + cudaMalloc: implicit device synchronisation) the first time a larger size is seen. */
+int kpn_reserve(kpn_ctx* ctx, long long max_rays, int max_samples);
 
 /* Debug: the device watchdog words of the tensor-core kernels.  Every barrier wait of those kernels gives up after ~2^20
  * suspended polls instead of hanging the GPU; out16 (host, may be NULL) receives [0] flag (!= 0: some wait gave up; results of

@@ -15,9 +15,11 @@ KPN_OK = 0
 KPN_MEM_DEVICE = 0
 KPN_MEM_HOST = 1
 KPN_NUM_LAYERS = 19
+KPN_NHWC_FEAT64, KPN_NHWC_FEAT8, KPN_NHWC_FEATTEX = 1, 2, 4
 
 EXPORTS = ["kpn_abi_version", "kpn_create", "kpn_destroy", "kpn_last_error", "kpn_set_weights", "kpn_set_scene",
-           "kpn_render", "kpn_query", "kpn_get_stats", "kpn_set_profiling", "kpn_selftest_umma", "kpn_selftest_umma2", "kpn_debug_timing", "kpn_debug_kmap"]
+           "kpn_render", "kpn_query", "kpn_get_stats", "kpn_set_profiling", "kpn_selftest_umma", "kpn_selftest_umma2", "kpn_debug_timing", "kpn_debug_kmap", "kpn_check_health", "kpn_reserve"]
+KPN_ABI_VERSION = 2
 
 c_float_p = C.POINTER(C.c_float)
 c_u8_p = C.POINTER(C.c_uint8)
@@ -42,13 +44,13 @@ class KpnScene(C.Structure):
                 ("feat_tex", C.c_void_p), ("ftex_c", C.c_int), ("ftex_h", C.c_int), ("ftex_w", C.c_int),
                 ("img", C.c_void_p), ("img_h", C.c_int), ("img_w", C.c_int),
                 ("fg", C.c_void_p), ("fg_h", C.c_int), ("fg_w", C.c_int),
-                ("mem", C.c_int)]
+                ("mem", C.c_int), ("layout", C.c_int)]
 
 
 class KpnTarget(C.Structure):
     _fields_ = [("K", C.c_void_p), ("RT", C.c_void_p), ("znear", C.c_float), ("zfar", C.c_float),
                 ("x0", C.c_int), ("y0", C.c_int), ("step", C.c_int), ("nx", C.c_int), ("ny", C.c_int),
-                ("mem", C.c_int)]
+                ("mem", C.c_int), ("step_y", C.c_int)]
 
 
 class KpnOpts(C.Structure):
@@ -64,7 +66,8 @@ class KpnOut(C.Structure):
 
 class KpnStats(C.Structure):
     _fields_ = [("samples_total", C.c_uint64), ("samples_valid", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("shade_launches", C.c_uint64), ("shade_ms", C.c_double)]
+                ("shade_launches", C.c_uint64), ("shade_ms", C.c_double), ("samples_coloured", C.c_uint64),
+                ("geo_ms", C.c_double)]
 
 
 _lib = None
@@ -81,6 +84,12 @@ def load() -> C.CDLL:
             "keypointnerf_b200 has no CPU or PyTorch fallback for the ray-march path.")
     lib = C.CDLL(LIB_PATH)
     lib.kpn_abi_version.restype = C.c_int
+    if lib.kpn_abi_version() != KPN_ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} has ABI version {lib.kpn_abi_version()}, this binding expects {KPN_ABI_VERSION}: rebuild it")
+    lib.kpn_check_health.argtypes = [C.c_void_p, C.c_void_p]
+    lib.kpn_check_health.restype = C.c_int
+    lib.kpn_reserve.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
+    lib.kpn_reserve.restype = C.c_int
     lib.kpn_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.kpn_create.restype = C.c_int
     lib.kpn_destroy.argtypes = [C.c_void_p]

@@ -73,6 +73,7 @@ struct kpn_ctx {
   DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in, ws_lat, ws_list2, ws_ert;
   unsigned long long launches = 0;
   bool profiling = false;
+  unsigned int* h_wd = nullptr;   // pinned host copy of the tensor-core kernels' watchdog words (refreshed by every render/query)
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   size_t ev_used = 0;
 };
@@ -115,6 +116,11 @@ extern "C" int kpn_create(int device, kpn_ctx** out) {
   if (!ok) { kpn_destroy(c); return KPN_ERR_CUDA; }
   cudaMemset(c->d_counters, 0, sizeof(int) * MAX_CHUNKS);
   cudaMemset(c->d_counters2, 0, sizeof(int) * MAX_CHUNKS);
+  if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_wd), 8 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess) {
+    kpn_destroy(c);
+    return KPN_ERR_CUDA;
+  }
+  memset(c->h_wd, 0, 8 * sizeof(unsigned int));
   *out = c;
   return KPN_OK;
 }
@@ -134,10 +140,37 @@ extern "C" void kpn_destroy(kpn_ctx* c) {
   c->ws_contrib.release(); c->ws_zfine.release(); c->ws_out.release(); c->ws_in.release();
   c->ws_lat.release(); c->ws_list2.release(); c->ws_ert.release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->h_wd) cudaFreeHost(c->h_wd);
   delete c;
 }
 
 extern "C" const char* kpn_last_error(const kpn_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+// Device watchdog (kpn_tc.cuh): a barrier wait that gives up raises a sticky device flag; every later wait of every later
+// tensor-core launch then aborts after a few polls, i.e. the engine keeps producing garbage until the flag is cleared.  Every
+// render/query ends with an asynchronous copy of the flag words into pinned host memory (wd_snapshot); every entry point starts
+// by looking at the last copy that has landed (wd_check): a raised flag is reported ONCE as KPN_ERR_CUDA and cleared on the
+// device (stream-ordered), which re-arms the engine for the calls that follow.
+static int wd_check(kpn_ctx* c, cudaStream_t st) {
+  volatile unsigned int* w = c->h_wd;
+  if (!w || w[0] == 0u) return KPN_OK;
+  const unsigned int blk = w[1], thr = w[2], tag = w[3], par = w[4];
+  for (int i = 0; i < 8; ++i) c->h_wd[i] = 0u;
+  KPN_CUDA(c, tc_watchdog_clear_async(st));
+  KPN_FAIL(c, KPN_ERR_CUDA, "device watchdog: a barrier wait of a tensor-core kernel gave up (block %u, thread %u, tag 0x%x, parity %u); "
+           "the results of that call (and of tensor-core calls enqueued after it) are invalid; the flag has been cleared",
+           blk, thr, tag, par);
+}
+static int wd_snapshot(kpn_ctx* c, cudaStream_t st) {
+  KPN_CUDA(c, tc_watchdog_read_async(c->h_wd, st));
+  return KPN_OK;
+}
+
+extern "C" int kpn_check_health(kpn_ctx* c, void* stream) {
+  if (!c) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  return wd_check(c, (cudaStream_t)stream);
+}
 
 // ---------------------------------------------------------------------------------------------
 // weights
@@ -265,6 +298,7 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
   DeviceGuard g(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!c->have_weights) KPN_FAIL(c, KPN_ERR_STATE, "kpn_set_weights must precede kpn_set_scene");
+  { int hrc = wd_check(c, st); if (hrc != KPN_OK) return hrc; }
   if (s->n_views < 1 || s->n_views > 3) KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "n_views=%d unsupported (1..3)", s->n_views);
   if (s->n_kpt != c->n_kpt) KPN_FAIL(c, KPN_ERR_ARG, "scene n_kpt=%d != weights n_kpt=%d", s->n_kpt, c->n_kpt);
   if (!s->KRT || !s->extrin || !s->kpt3d || !s->bounds || !s->feat64 || !s->feat8 || !s->feat_tex || !s->img)
@@ -298,6 +332,18 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
     if (M.H < 1 || M.W < 1) KPN_FAIL(c, KPN_ERR_ARG, "map %d has empty extent", m);
     size_t in_bytes = (size_t)V * M.C * M.H * M.W * sizeof(float);
     size_t out_bytes = (size_t)V * M.Cp * M.H * M.W * sizeof(float);
+    if (m < 3 && ((s->layout >> m) & 1)) {
+      // already [V][H][W][C] (channels-last encoder output, C == Cp): no re-layout pass.  Device maps are gathered from in
+      // place (the caller keeps them alive and unchanged until the next kpn_set_scene); host maps are uploaded as they are.
+      const void* ptr = M.src;
+      if (s->mem == KPN_MEM_HOST) {
+        KPN_CUDA(c, c->atlas[m].reserve(out_bytes));
+        KPN_CUDA(c, cudaMemcpyAsync(c->atlas[m].p, M.src, in_bytes, cudaMemcpyHostToDevice, st));
+        ptr = c->atlas[m].p;
+      }
+      descs[m]->ptr = ptr; descs[m]->C = M.Cp; descs[m]->H = M.H; descs[m]->W = M.W;
+      continue;
+    }
     const float* dsrc = M.src;
     if (s->mem == KPN_MEM_HOST) {
       KPN_CUDA(c, c->stage[m].reserve(in_bytes));
@@ -332,20 +378,23 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
 // ---------------------------------------------------------------------------------------------
 static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_mode, int slot, float* out5,
                        uint8_t* valid_out, int engine, cudaStream_t st, const ErtSegment& ert = ErtSegment{0, 0, nullptr, 0.0f}) {
-  const bool use_tc = engine != 1 && c->tc_weights && tc_supported(c->scene_views, c->n_kpt, c->sp_level);
+  const bool use_tc = engine != 1;
+  if (use_tc && !(c->tc_weights && tc_supported(c->scene_views, c->n_kpt, c->sp_level)))
+    KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "the tensor-core engine covers n_views == 3, n_kpt in {18, 24}, sp_level == 3; this scene has "
+             "n_views=%d n_kpt=%d sp_level=%d: request engine = 1 (fp32 CUDA-core engine, ~25x slower) explicitly",
+             c->scene_views, c->n_kpt, c->sp_level);
   KPN_CUDA(c, c->ws_list.reserve((size_t)n * sizeof(int)));
   int* counter = c->d_counters + slot;
   KPN_CUDA(c, launch_compact(c->d_scene, src, n, query_mode, c->ws_list.as<int>(), counter, out5, valid_out, ert, st));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr;   // start | after the geometry kernel | stop
   if (c->profiling) {
-    if (c->ev_used + 2 > c->ev_pool.size()) {
-      cudaEvent_t a, b;
+    while (c->ev_used + 3 > c->ev_pool.size()) {
+      cudaEvent_t a;
       KPN_CUDA(c, cudaEventCreate(&a));
-      KPN_CUDA(c, cudaEventCreate(&b));
-      c->ev_pool.push_back(a); c->ev_pool.push_back(b);
+      c->ev_pool.push_back(a);
     }
-    e0 = c->ev_pool[c->ev_used]; e1 = c->ev_pool[c->ev_used + 1];
-    c->ev_used += 2;
+    e0 = c->ev_pool[c->ev_used]; em = c->ev_pool[c->ev_used + 1]; e1 = c->ev_pool[c->ev_used + 2];
+    c->ev_used += 3;
     KPN_CUDA(c, cudaEventRecord(e0, st));
   }
   if (use_tc) {
@@ -353,14 +402,57 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_
     KPN_CUDA(c, c->ws_list2.reserve((size_t)n * 8));
     KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), c->wlo.as<uint8_t>(), engine == 2 ? 0 : 1, c->n_kpt,
                                 src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->ws_lat.p, c->ws_list2.p,
-                                c->d_counters2 + slot, c->num_sms, st));
+                                c->d_counters2 + slot, c->num_sms, em, st));
     c->launches++;
   }
-  else
+  else {
     KPN_CUDA(c, launch_shade_simt(c->d_scene, c->d_wf32, src, c->ws_list.as<int>(), counter, n, query_mode, out5,
                                   c->num_sms, st));
+    if (c->profiling) KPN_CUDA(c, cudaEventRecord(em, st));
+  }
   if (c->profiling) KPN_CUDA(c, cudaEventRecord(e1, st));
   c->launches += 2;
+  return KPN_OK;
+}
+
+// rays per chunk: bounded by the per-sample workspace; fewer, larger launches amortise the persistent kernels' prologue (weight
+// load) and tail (measured 4 / 8 / 32 Mi samples: 30.5 / 30.2 / 30.0 ms per 512x512x128 frame).  KPN_CHUNK_SAMPLES overrides
+// the default of 32 Mi samples.
+static long long chunk_rays(long long R, int Smax) {
+  static const long long chunk_samples = [] {
+    const char* e = getenv("KPN_CHUNK_SAMPLES");
+    long long v = e ? atoll(e) : 0;
+    return v >= (1ll << 16) && v <= (1ll << 28) ? v : (32ll << 20);
+  }();
+  long long Rc = chunk_samples / Smax;
+  Rc = (Rc / 128) * 128;
+  if (Rc < 128) Rc = 128;
+  return Rc > R ? R : Rc;
+}
+
+// every per-chunk workspace buffer of a render of Rc rays x (Sc coarse, Smax total) samples
+static int reserve_render(kpn_ctx* c, long long Rc, int Sc, int Smax, bool fine, bool contrib, bool ert) {
+  const size_t n = (size_t)Rc * Smax;
+  KPN_CUDA(c, c->ws_rayd.reserve((size_t)Rc * 3 * sizeof(float)));
+  KPN_CUDA(c, c->ws_raynf.reserve((size_t)Rc * 2 * sizeof(float)));
+  KPN_CUDA(c, c->ws_z.reserve((size_t)Rc * Sc * sizeof(float)));
+  KPN_CUDA(c, c->ws_rgba.reserve(n * 5 * sizeof(float)));
+  KPN_CUDA(c, c->ws_list.reserve(n * sizeof(int)));
+  KPN_CUDA(c, c->ws_lat.reserve(n * 48));
+  KPN_CUDA(c, c->ws_list2.reserve(n * 8));
+  if (fine || contrib) KPN_CUDA(c, c->ws_contrib.reserve((size_t)Rc * Sc * sizeof(float)));
+  if (fine) KPN_CUDA(c, c->ws_zfine.reserve(n * sizeof(float)));
+  if (ert) KPN_CUDA(c, c->ws_ert.reserve((size_t)Rc * sizeof(float)));
+  return KPN_OK;
+}
+
+extern "C" int kpn_reserve(kpn_ctx* c, long long max_rays, int max_samples) {
+  if (!c || max_rays < 1 || max_samples < 1) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  const long long Rc = chunk_rays(max_rays, max_samples);
+  int rc = reserve_render(c, Rc, max_samples, max_samples, true, true, true);
+  if (rc != KPN_OK) return rc;
+  KPN_CUDA(c, c->ws_out.reserve((size_t)max_rays * 11 * sizeof(float)));   // host-output staging: 3+1+1+3+1+1+1 planes
   return KPN_OK;
 }
 
@@ -377,10 +469,11 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
   DeviceGuard g(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!c->have_scene) KPN_FAIL(c, KPN_ERR_STATE, "kpn_set_scene must precede kpn_render");
+  { int hrc = wd_check(c, st); if (hrc != KPN_OK) return hrc; }
   const int Sc = op->sample_per_ray_c, Sf = op->fine ? op->sample_per_ray_f : 0;
   if (Sc < 1 || Sc > max_coarse_samples()) KPN_FAIL(c, KPN_ERR_ARG, "sample_per_ray_c=%d out of range", Sc);
   if (op->fine && (Sc < 3 || Sf < 1 || Sf > 1024)) KPN_FAIL(c, KPN_ERR_ARG, "fine pass needs S_c>=3 and 1<=S_f<=1024");
-  if (tg->nx < 1 || tg->ny < 1 || tg->step < 1) KPN_FAIL(c, KPN_ERR_ARG, "empty pixel lattice");
+  if (tg->nx < 1 || tg->ny < 1 || tg->step < 1 || tg->step_y < 0) KPN_FAIL(c, KPN_ERR_ARG, "empty pixel lattice");
   if (!tg->K || !tg->RT) KPN_FAIL(c, KPN_ERR_ARG, "null target camera");
   const long long R = (long long)tg->nx * tg->ny;
   const int Smax = Sc + Sf;
@@ -393,6 +486,7 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
   DevTarget ht;
   memset(&ht, 0, sizeof(ht));
   ht.znear = tg->znear; ht.zfar = tg->zfar; ht.x0 = tg->x0; ht.y0 = tg->y0; ht.step = tg->step; ht.nx = tg->nx; ht.ny = tg->ny;
+  ht.step_y = tg->step_y > 0 ? tg->step_y : tg->step;
   KPN_CUDA(c, cudaMemcpyAsync(c->d_target, &ht, sizeof(ht), cudaMemcpyHostToDevice, st));
   KPN_CUDA(c, launch_prep_target(c->d_raw_target, c->d_target, st));
   c->launches++;
@@ -413,35 +507,19 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
     for (int i = 0; i < 7; ++i) dev[i] = user[i];
   }
 
-  // rays per chunk: bounded by the per-sample workspace (20 B/sample rgba + lists); fewer, larger launches amortise the
-  // persistent kernels' prologue (weight load) and tail (measured 4 / 8 / 32 Mi: 30.5 / 30.2 / 30.0 ms per 512x512x128 frame).
-  // KPN_CHUNK_SAMPLES overrides the default of 32 Mi samples (2.7 GB of workspace).
-  static const long long chunk_samples = [] {
-    const char* e = getenv("KPN_CHUNK_SAMPLES");
-    long long v = e ? atoll(e) : 0;
-    return v >= (1ll << 16) && v <= (1ll << 28) ? v : (32ll << 20);
-  }();
-  long long Rc = chunk_samples / Smax;
-  Rc = (Rc / 128) * 128;
-  if (Rc < 128) Rc = 128;
-  if (Rc > R) Rc = R;
+  const long long Rc = chunk_rays(R, Smax);
   const long long nchunks = (R + Rc - 1) / Rc;
   if (nchunks * 4 > MAX_CHUNKS) KPN_FAIL(c, KPN_ERR_ARG, "frame too large for one call (%lld chunks)", nchunks);
-  KPN_CUDA(c, c->ws_rayd.reserve((size_t)Rc * 3 * sizeof(float)));
-  KPN_CUDA(c, c->ws_raynf.reserve((size_t)Rc * 2 * sizeof(float)));
-  KPN_CUDA(c, c->ws_z.reserve((size_t)Rc * Sc * sizeof(float)));
-  KPN_CUDA(c, c->ws_rgba.reserve((size_t)Rc * Smax * 5 * sizeof(float)));
   const bool need_contrib = op->fine || out->contrib;
-  if (need_contrib) KPN_CUDA(c, c->ws_contrib.reserve((size_t)Rc * Sc * sizeof(float)));
-  if (op->fine) KPN_CUDA(c, c->ws_zfine.reserve((size_t)Rc * Smax * sizeof(float)));
-  int rc = begin_counters(c, st);
+  const bool ert_on = op->ert_eps > 0.0f;
+  int rc = reserve_render(c, Rc, Sc, Smax, op->fine != 0, need_contrib, ert_on);
+  if (rc != KPN_OK) return rc;
+  rc = begin_counters(c, st);
   if (rc != KPN_OK) return rc;
   cudaMemcpyKind okind = host_out ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   // Shade the S samples of nr rays into ws_rgba.  Early-ray termination (ert_eps > 0, S >= 8): the front half of every ray is
   // shaded and composited first; rays whose transmittance behind it is < ert_eps skip the back half (their remaining
   // contribution to any channel is < ert_eps; the reference has no such option, ert_eps = 0 reproduces it exactly).
-  const bool ert_on = op->ert_eps > 0.0f;
-  if (ert_on) KPN_CUDA(c, c->ws_ert.reserve((size_t)Rc * sizeof(float)));
   auto march = [&](const SampleSrc& src, int nr, int S, const float* zbuf, int slot) -> int {
     const long long n = (long long)nr * S;
     if (!ert_on || S < 8) return shade_batch(c, src, n, 0, slot, c->ws_rgba.as<float>(), nullptr, op->engine, st);
@@ -496,7 +574,7 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
     for (int i = 0; i < 7; ++i)
       if (user[i]) KPN_CUDA(c, cudaMemcpyAsync(user[i], dev[i], (size_t)planes[i] * R * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
-  return KPN_OK;
+  return wd_snapshot(c, st);
 }
 
 extern "C" int kpn_query(kpn_ctx* c, const float* pts, const float* view, int n, float* out5, uint8_t* valid, int mem,
@@ -505,6 +583,7 @@ extern "C" int kpn_query(kpn_ctx* c, const float* pts, const float* view, int n,
   DeviceGuard g(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!c->have_scene) KPN_FAIL(c, KPN_ERR_STATE, "kpn_set_scene must precede kpn_query");
+  { int hrc = wd_check(c, st); if (hrc != KPN_OK) return hrc; }
   int rc = begin_counters(c, st);
   if (rc != KPN_OK) return rc;
   if (n == 0) return KPN_OK;
@@ -541,36 +620,39 @@ extern "C" int kpn_query(kpn_ctx* c, const float* pts, const float* view, int n,
     KPN_CUDA(c, cudaMemcpyAsync(out5, dout, (size_t)n * 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (valid) KPN_CUDA(c, cudaMemcpyAsync(valid, dvalid, (size_t)n, cudaMemcpyDeviceToHost, st));
   }
-  return KPN_OK;
+  return wd_snapshot(c, st);
 }
 
 extern "C" int kpn_get_stats(kpn_ctx* c, kpn_stats* stats, void* stream) {
   if (!c || !stats) return KPN_ERR_ARG;
   DeviceGuard g(c->device);
   cudaStream_t st = (cudaStream_t)stream;
-  std::vector<int> h(c->counters_used > 0 ? c->counters_used : 1, 0);
-  if (c->counters_used > 0)
+  std::vector<int> h(c->counters_used > 0 ? c->counters_used : 1, 0), h2(c->counters_used > 0 ? c->counters_used : 1, 0);
+  if (c->counters_used > 0) {
     KPN_CUDA(c, cudaMemcpyAsync(h.data(), c->d_counters, sizeof(int) * c->counters_used, cudaMemcpyDeviceToHost, st));
+    KPN_CUDA(c, cudaMemcpyAsync(h2.data(), c->d_counters2, sizeof(int) * c->counters_used, cudaMemcpyDeviceToHost, st));
+  }
+  KPN_CUDA(c, tc_watchdog_read_async(c->h_wd, st));
   KPN_CUDA(c, cudaStreamSynchronize(st));
-  unsigned long long valid = 0;
-  for (int i = 0; i < c->counters_used; ++i) valid += (unsigned long long)h[i];
+  unsigned long long valid = 0, coloured = 0;
+  for (int i = 0; i < c->counters_used; ++i) { valid += (unsigned long long)h[i]; coloured += (unsigned long long)h2[i]; }
   stats->samples_total = c->last_total;
   stats->samples_valid = valid;
+  stats->samples_coloured = coloured;
   stats->kernel_launches = c->launches;
-  double ms = 0.0;
-  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
-    float t = 0.0f;
-    KPN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[i], c->ev_pool[i + 1]));
+  double ms = 0.0, gms = 0.0;
+  for (size_t i = 0; i + 2 < c->ev_used; i += 3) {   // triples: start, after the geometry kernel, stop
+    float t = 0.0f, tg = 0.0f;
+    KPN_CUDA(c, cudaEventElapsedTime(&t, c->ev_pool[i], c->ev_pool[i + 2]));
+    KPN_CUDA(c, cudaEventElapsedTime(&tg, c->ev_pool[i], c->ev_pool[i + 1]));
     ms += (double)t;
+    gms += (double)tg;
   }
-  stats->shade_launches = c->ev_used / 2;
+  stats->shade_launches = c->ev_used / 3;
   stats->shade_ms = ms;
+  stats->geo_ms = gms;
   c->ev_used = 0;
-  unsigned int wd[8];
-  KPN_CUDA(c, tc_watchdog_read(wd, false));
-  if (wd[0]) KPN_FAIL(c, KPN_ERR_CUDA, "device watchdog: a barrier wait gave up (block %u, thread %u, tag 0x%x, parity %u); results are invalid",
-                      wd[1], wd[2], wd[3], wd[4]);
-  return KPN_OK;
+  return wd_check(c, st);
 }
 
 // Debug hook.  out16[0..7] receive the device watchdog words of the tensor-core kernels (out16[0] != 0: a barrier wait gave

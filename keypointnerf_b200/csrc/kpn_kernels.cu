@@ -9,6 +9,7 @@
 //   shade_simt     per-sample gather + keypoint encoding + MLPs for tiles of 64 valid samples
 //   composite      alpha compositing along the ray
 //   importance     inverse-CDF resampling + merge with the coarse depths
+#include <atomic>
 #include "kpn_device.cuh"
 #include "kpn_launch.h"
 
@@ -137,7 +138,7 @@ __global__ void rays_kernel(const DevScene* __restrict__ sc, const DevTarget* __
   if (i >= nr) return;
   int r = r0 + i;
   int ix = r % tg->nx, iy = r / tg->nx;
-  float px = (float)(tg->x0 + tg->step * ix), py = (float)(tg->y0 + tg->step * iy);
+  float px = (float)(tg->x0 + tg->step * ix), py = (float)(tg->y0 + tg->step_y * iy);
   float d[3], n, f;
   ray_for_pixel(*sc, *tg, px, py, d, n, f);
   ray_d[3 * i + 0] = d[0]; ray_d[3 * i + 1] = d[1]; ray_d[3 * i + 2] = d[2];
@@ -683,13 +684,13 @@ cudaError_t launch_compact(const DevScene* sc, const SampleSrc& src, long long n
 cudaError_t launch_shade_simt(const DevScene* sc, const DevWeightsF32* W, const SampleSrc& src, const int* list,
                               const int* counter, long long n_max, int query_mode, float* out5, int num_sms,
                               cudaStream_t st) {
-  static bool attr_set[64] = {};   // function attributes are per device
+  static std::atomic<bool> attr_set[64];   // function attributes are per device (setting them twice is harmless)
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(shade_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHADE_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   int grid = grid_for(n_max, TS, num_sms);
   shade_simt_kernel<<<grid, NT, SHADE_SMEM_BYTES, st>>>(sc, W, src, list, counter, query_mode, out5);

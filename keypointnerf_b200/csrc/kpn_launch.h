@@ -23,9 +23,11 @@ cudaError_t launch_importance(const float* contrib, const float* z, int nr, int 
 // geometry stages; lat_scratch: n_max x 48 bytes, list2: n_max x int2, count2: device int (zeroed by the caller).
 cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term, int n_kpt,
                             const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
-                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st);
+                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaEvent_t after_geo, cudaStream_t st);
 size_t tc_pair_blob_bytes(int n_kpt);
 cudaError_t tc_watchdog_read(unsigned int out[8], bool reset);
+cudaError_t tc_watchdog_read_async(unsigned int* pinned_out8, cudaStream_t st);   // stream-ordered copy into pinned host memory
+cudaError_t tc_watchdog_clear_async(cudaStream_t st);
 size_t tc_weight_blob_bytes(int n_kpt);
 size_t tc_weight_lo_bytes(int n_kpt);
 bool tc_supported(int n_views, int n_kpt, int sp_level);

@@ -23,6 +23,7 @@
 //          (biases as K rows, two-term weights W_hi + W_lo; tensor-memory placement: geo_dcol)
 //   colour 12 RE1 16->35 R0->R1 | 6 BASE0 105->64 R0->R1 | 7 BASE1 64->32 R1->R0 | 8 VIS1A 32->32 R0->R1 | 9 VIS1B 32->33 R1->R0
 //          10 VIS2A 32->32 R0->R1 | 11 OUT0 37->16 R1->R0     (R0/R1: the slot's two 64-column regions, in-place epilogues)
+#include <atomic>
 #include <cstdlib>
 #include "kpn_device.cuh"
 #include "kpn_launch.h"
@@ -1120,19 +1121,19 @@ bool tc_supported(int n_views, int n_kpt, int sp_level) { return n_views == 3 &&
 template <int NK>
 static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term,
                                   const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
-                                  uint4* lat, int2* list2, int* count2, int num_sms, cudaStream_t st) {
+                                  uint4* lat, int2* list2, int* count2, int num_sms, cudaEvent_t after_geo, cudaStream_t st) {
   constexpr TcPlan plan = make_tc_plan(NK);
   const size_t smem_geo = plan.st[GEO_NSTAGE].off + (geo_pref(NK) ? (size_t)NSLOT * GEO_FW * 128 * 4 : 0);
   const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
-  static bool attr[64] = {};   // function attributes are per device
+  static std::atomic<bool> attr[64];   // function attributes are per device (zero-initialised; setting them twice is harmless)
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr[dev]) {
+  if (dev < 0 || dev >= 64 || !attr[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(shade_geo_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_geo);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(shade_color_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr[dev] = true;
+    if (dev >= 0 && dev < 64) attr[dev].store(true, std::memory_order_release);
   }
   const long long max_tiles = (n_max + SPT - 1) / SPT;
   long long pairs = (max_tiles + 2 * NSLOT - 1) / (2 * NSLOT);   // clusters that can have work
@@ -1146,6 +1147,7 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
                                                            count2, relaxed_arrive);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (after_geo) { e = cudaEventRecord(after_geo, st); if (e != cudaSuccess) return e; }
   long long g = (max_tiles + CSLOT - 1) / CSLOT;
   grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
   shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, count2, lat, out5);
@@ -1154,12 +1156,12 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
 
 cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term, int n_kpt,
                             const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
-                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaStream_t st) {
+                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaEvent_t after_geo, cudaStream_t st) {
   if (n_kpt == 18)
     return launch_tc_impl<18>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
-                              (int2*)list2, count2, num_sms, st);
+                              (int2*)list2, count2, num_sms, after_geo, st);
   return launch_tc_impl<24>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
-                            (int2*)list2, count2, num_sms, st);
+                            (int2*)list2, count2, num_sms, after_geo, st);
 }
 
 // Watchdog state of this module's kernels: out[0] != 0 -> some barrier wait gave up at block out[1], thread out[2], tag out[3].
@@ -1170,6 +1172,16 @@ cudaError_t tc_watchdog_read(unsigned int out[8], bool reset) {
     e = cudaMemcpyToSymbol(tc::kpn_wd, z, sizeof(z));
   }
   return e;
+}
+
+cudaError_t tc_watchdog_read_async(unsigned int* pinned_out8, cudaStream_t st) {
+  return cudaMemcpyFromSymbolAsync(pinned_out8, tc::kpn_wd, 8 * sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, st);
+}
+cudaError_t tc_watchdog_clear_async(cudaStream_t st) {
+  void* p = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&p, tc::kpn_wd);
+  if (e != cudaSuccess) return e;
+  return cudaMemsetAsync(p, 0, 8 * sizeof(unsigned int), st);
 }
 
 size_t tc_pair_blob_bytes(int n_kpt) { return 2 * (size_t)make_tc_plan(n_kpt).st[GEO_NSTAGE].off; }

@@ -55,6 +55,7 @@ struct DevTarget {
   float o[3];              // camera centre -t^T R (src/model.py:1036)
   float znear, zfar;
   int x0, y0, step, nx, ny;
+  int step_y;              // lattice step along y (== step for the reference's square lattices)
 };
 
 // Packed dense layers for the fp32 SIMT engine: Wt [K][ldw] transposed, zero padded to ldw = roundup(N,32).

@@ -2,8 +2,13 @@
 
 The reference has no multi-GPU rendering; rays are independent, so the only
 exchange step is ONE all-gather of the rendered shards (NCCL over NVLink on the GPU box, gloo in
-the CPU tests).  Two partitions:
-  * ``row_shard`` / ``gather_rows``: one frame split into contiguous row bands (BASELINE config 4);
+the CPU tests).  Partitions:
+  * ``lattice_shape`` / ``gather_lattice`` / ``render_frame_lattice_sharded``: one frame split into the
+    stride-lattice phases the reference itself renders a frame in (``src/model.py:916-923``), one
+    phase per rank: every phase sees the whole image, so the ranks are load-balanced by construction
+    (BASELINE config 4);
+  * ``row_shard`` / ``gather_rows`` / ``render_frame_row_sharded``: contiguous row bands (frames whose
+    size the lattice does not divide);
   * ``gather_views``: one novel view per rank (BASELINE config 5, render_dynamic.py-style sweep).
 """
 from __future__ import annotations
@@ -72,6 +77,55 @@ def gather_rows(shard: torch.Tensor, height: int, rank: int, world: int) -> torc
     return torch.cat(bands, dim=-2)
 
 
+def lattice_shape(world: int):
+    """(sy, sx) with sy * sx == world, as square as possible, sx >= sy: rank r renders the pixels
+    (x, y) with x % sx == r % sx and y % sy == r // sx."""
+    sy = 1
+    for d in range(1, int(world ** 0.5) + 1):
+        if world % d == 0:
+            sy = d
+    return sy, world // sy
+
+
+def lattice_phase(rank: int, world: int):
+    """(y0, x0, step_y, step_x) of rank ``rank``'s lattice phase."""
+    sy, sx = lattice_shape(world)
+    return rank // sx, rank % sx, sy, sx
+
+
+def interleave_lattice(stack: torch.Tensor, world: int) -> torch.Tensor:
+    """(world, ..., h, w) lattice phases -> (..., h*sy, w*sx): the inverse of the partition (the reference's
+    ``pixel_shuffle`` assembly, ``src/model.py:935-938``)."""
+    sy, sx = lattice_shape(world)
+    lead = tuple(stack.shape[1:-2])
+    h, w = stack.shape[-2:]
+    x = stack.reshape(sy, sx, *lead, h, w)
+    nd = len(lead)
+    perm = [2 + i for i in range(nd)] + [nd + 2, 0, nd + 3, 1]   # (..., h, sy, w, sx)
+    return x.permute(*perm).reshape(*lead, h * sy, w * sx)
+
+
+def gather_lattice(shard: torch.Tensor, world: int) -> torch.Tensor:
+    """All-gather the ranks' lattice phases (..., H/sy, W/sx) into the full (..., H, W) image on every rank."""
+    if world == 1:
+        return shard
+    return interleave_lattice(_all_gather_stack(shard, world), world)
+
+
+def render_frame_lattice_sharded(marcher, *, K, RT, znear, zfar, width: int, height: int, rank: int, world: int,
+                                 **render_kw) -> dict:
+    """BASELINE config 4: ONE target frame, rank r renders lattice phase r (scene already bound on every rank), then ONE
+    all-gather per output plane and a local un-permute.  Bit-identical to the single-GPU frame: rays are independent."""
+    y0, x0, sy, sx = lattice_phase(rank, world)
+    if height % sy or width % sx:
+        return render_frame_row_sharded(marcher, K=K, RT=RT, znear=znear, zfar=zfar, width=width, height=height,
+                                        rank=rank, world=world, **render_kw)
+    res = marcher.render(K=K, RT=RT, znear=znear, zfar=zfar, x0=x0, y0=y0, step=sx, step_y=sy, nx=width // sx,
+                         ny=height // sy, out_device="cuda", **render_kw)
+    return {k: gather_lattice(v, world) for k, v in res.items() if v.dim() >= 2 and v.shape[-2] == height // sy
+            and v.shape[-1] == width // sx}
+
+
 def gather_views(frame: torch.Tensor, world: int) -> torch.Tensor:
     """All-gather one rendered frame per rank into (world, ...) on every rank."""
     if world == 1:
@@ -80,8 +134,9 @@ def gather_views(frame: torch.Tensor, world: int) -> torch.Tensor:
 
 
 def render_frame_row_sharded(marcher, *, K, RT, znear, zfar, width: int, height: int, rank: int, world: int, **render_kw) -> dict:
-    """BASELINE config 4: ONE target frame split into contiguous row bands, one band per rank (the scene must already be bound
-    to every rank's ``RayMarcher``), then one all-gather per output plane.  ``render_kw`` goes to ``RayMarcher.render``
+    """ONE target frame split into contiguous row bands, one band per rank (the scene must already be bound
+    to every rank's ``RayMarcher``), then one all-gather per output plane; not load-balanced (the top and bottom bands are
+    mostly empty space): ``render_frame_lattice_sharded`` is the partition BASELINE config 4 uses.  ``render_kw`` goes to ``RayMarcher.render``
     (``S_c``, ``S_f``, ``fine``, ``engine``, ``ert_eps``).  Returns full-frame tensors on every rank, bit-identical to the
     single-GPU frame because rays are independent (``tests/test_gpu_parity.py`` checks strided/offset passes against the frame)."""
     y0, ny = row_shard(height, rank, world)

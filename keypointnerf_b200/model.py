@@ -7,10 +7,11 @@ hot-path networks (reference ``src/model.py:559-609``), ``query`` (690), and the
 positional order and ``**config`` keys.  All per-sample arithmetic runs in the CUDA
 library behind ``include/kpnerf_b200.h``; this file only marshals tensors.
 
-Out of scope here: the 2-D image encoders (``geo_encoder``,
-``tex_encoder``) and the training ``forward``.  Encoders can be attached by assigning
-modules to ``net.geo_encoder`` / ``net.tex_encoder``; otherwise pass the feature maps
-explicitly, as the reference's tile entry already allows (``feat_geo``, ``feat_tex``).
+The 2-D image encoders (``geo_encoder``, ``tex_encoder``; ``keypointnerf_b200/encoders.py``) carry the
+reference's parameter names, run channels-last and hand their outputs to the kernels without a
+re-layout pass; their feature maps are cached per source-image set.  A reference checkpoint loads
+with ``strict=True`` (``vgg_loss.*`` entries, which only the training loss reads, are accepted and
+dropped).  Out of scope: the training ``forward``.
 """
 from __future__ import annotations
 
@@ -19,6 +20,7 @@ import copy
 import torch
 import torch.nn as nn
 
+from . import encoders as enc
 from .renderer import RayMarcher
 
 
@@ -100,7 +102,7 @@ class SpatialEncoder(nn.Module):
         return (1 + 2 * self.sp_level) * self.n_kpt
 
 
-_HOT_PREFIXES = ("mlp_geo.", "mlp_tex.", "ibr_compress_gfeat.")
+_HOT_MODULES = ("mlp_geo", "mlp_tex", "ibr_compress_gfeat")
 
 
 class KeypointNeRF(nn.Module):
@@ -117,8 +119,10 @@ class KeypointNeRF(nn.Module):
         self.mlp_tex = IBRRenderingHead(**model_cfg["mlp_tex_args"]["args"])
         self.ibr_compress_gfeat = nn.Linear(model_cfg["mlp_tex_args"]["gcompress"]["in_ch"],
                                             model_cfg["mlp_tex_args"]["gcompress"]["out_ch"])
-        self.geo_encoder = None   # attach HGFilterV2-compatible module to use attach_geo_feat
-        self.tex_encoder = None   # attach ResBlkEncoder-compatible module to use attach_tex_feat
+        # image encoders (reference src/model.py:575,598): built when the config describes them, channels-last
+        self.geo_encoder = enc.to_channels_last(enc.HGFilterV2(**model_cfg["geo_args"])) if "geo_args" in model_cfg else None
+        self.tex_encoder = enc.to_channels_last(enc.ResBlkEncoder(**model_cfg["tex_args"])) if "tex_args" in model_cfg else None
+        self._geo_cache, self._tex_cache = enc.FeatureCache(), enc.FeatureCache()
         self.sp_encoder_postfusion = None
         self.ds_geo = model_cfg.get("ds_geo", 0)
         self.ds_tex = model_cfg.get("ds_tex", 0)
@@ -132,6 +136,7 @@ class KeypointNeRF(nn.Module):
         self._marcher = None
         self._w_key = None
         self._scene_key = None
+        self._last_bounds = None
         self.engine = 0
 
     # ---- feature caching (reference src/model.py:642-688) -----------------------------------------
@@ -145,34 +150,66 @@ class KeypointNeRF(nn.Module):
         self.attach_geo_feat(im)
         self.attach_tex_feat(im)
 
+    @staticmethod
+    def _encode(module, im, n_down):
+        """avg-pool ``n_down`` times, map [0,1] -> [-1,1], run the encoder channels-last; the outputs' storage is
+        [V][H][W][C], the layout the kernels gather from (no re-layout pass in kpn_set_scene)."""
+        if im.dim() == 5:
+            im = im.view(-1, *im.shape[2:])
+        x = im.contiguous(memory_format=torch.channels_last)
+        for _ in range(n_down):
+            x = torch.nn.functional.avg_pool2d(x, 2, stride=2)
+        with torch.no_grad():
+            out = module(2.0 * x - 1.0)
+        return [enc.nhwc_view(o) for o in out] if isinstance(out, (list, tuple)) else enc.nhwc_view(out)
+
     def attach_geo_feat(self, im, return_val=False):
+        """Reference ``src/model.py:653-667``.  The maps of the last source-image set are cached: the reference re-runs the
+        encoders for every rendered camera (``src/model.py:913-914`` after 479), a camera sweep here runs them once."""
         if self.geo_encoder is None:
-            raise RuntimeError("no geo_encoder attached: pass feat_geo explicitly (image encoders are outside the "
-                               "ray-march hot path, SURVEY.md section 8f)")
+            raise RuntimeError("this model was built without geo_args: pass feat_geo explicitly")
         if not return_val:
             self.im = im.clone()
-        if im.dim() == 5:
-            im = im.view(-1, *im.shape[2:])
-        for _ in range(self.ds_geo):
-            im = torch.nn.functional.avg_pool2d(im, 2, stride=2)
-        self.feat_geo = self.geo_encoder(2.0 * im - 1.0)
+        feat = self._geo_cache.get(im, lambda x: self._encode(self.geo_encoder, x, self.ds_geo))
         if return_val:
-            return self.feat_geo
+            return feat
+        self.feat_geo = feat
 
     def attach_tex_feat(self, im, return_val=False):
+        """Reference ``src/model.py:669-680``."""
         if self.tex_encoder is None:
             return None
-        if im.dim() == 5:
-            im = im.view(-1, *im.shape[2:])
-        for _ in range(self.ds_tex):
-            im = torch.nn.functional.avg_pool2d(im, 2, stride=2)
-        self.feat_tex = self.tex_encoder(2.0 * im - 1.0)
+        feat = self._tex_cache.get(im, lambda x: self._encode(self.tex_encoder, x, self.ds_tex))
         if return_val:
-            return self.feat_tex
+            return feat
+        self.feat_tex = feat
 
     def detach_im_feat(self):
         self.feat_geo = None
         self.feat_tex = None
+        self._geo_cache.clear()
+        self._tex_cache.clear()
+
+    def train(self, mode: bool = True):
+        self._geo_cache.clear()    # the encoder weights may change between calls while training
+        self._tex_cache.clear()
+        return super().train(mode)
+
+    # ---- checkpoints (reference load_ckpt: strict load_state_dict, src/model.py:113-117) ----------
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # The reference's model also owns vgg_loss (a frozen VGG19 the training loss reads, src/model.py:608) and, in some
+        # configs, encoders this instance was built without: accept those entries and drop them, so that a strict load of a
+        # reference checkpoint succeeds.  Everything the render path uses is still checked strictly.
+        ignored = ["vgg_loss.", "sp_encoder_postfusion."]
+        if self.geo_encoder is None:
+            ignored.append("geo_encoder.")
+        if self.tex_encoder is None:
+            ignored.append("tex_encoder.")
+        for k in [k for k in state_dict if k.startswith(prefix) and k[len(prefix):].startswith(tuple(ignored))]:
+            del state_dict[k]
+        self._geo_cache.clear()
+        self._tex_cache.clear()
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
     # ---- marshalling -----------------------------------------------------------------------------
     def _device_index(self):
@@ -187,7 +224,10 @@ class KeypointNeRF(nn.Module):
             self._marcher = RayMarcher(dev)
             self._w_key = None
             self._scene_key = None
-        hot = {k: v for k, v in self.state_dict().items() if k.startswith(_HOT_PREFIXES)}
+        hot = {}
+        for name in _HOT_MODULES:   # only the networks the ray-march reads (not the 28 M encoder parameters)
+            for k, v in getattr(self, name).state_dict().items():
+                hot[f"{name}.{k}"] = v
         key = tuple((k, v.data_ptr(), v._version) for k, v in hot.items())
         if key != self._w_key:
             sp = self.sp_encoder
@@ -200,7 +240,7 @@ class KeypointNeRF(nn.Module):
     def marcher_dtype(self) -> str:
         """Arithmetic type of the dense layers in the selected engine."""
         sp = self.sp_encoder
-        tc = self.engine != 1 and sp.n_kpt in (18, 24) and sp.sp_level == 3
+        tc = self.engine != 1
         return "fp16 operands, fp32 accumulate (tcgen05)" if tc else "fp32"
 
     def _bind_scene(self, cam, feat_geo, feat_tex, sp_data, img, fg_mask, bounds):
@@ -217,7 +257,13 @@ class KeypointNeRF(nn.Module):
                         width=cam["width"], height=cam["height"], znear=cam["znear"], zfar=cam["zfar"],
                         nml_scale=cam.get("nml_scale", 100.0))
             self._scene_key = key
+        self._last_bounds = bounds
         return m
+
+    def invalidate_scene(self):
+        """Force the next render/query to re-bind the scene (the cache key is tensor identity + version: call this after
+        writing into a bound tensor through a view that does not bump its version)."""
+        self._scene_key = None
 
     # ---- query (reference src/model.py:690-782) --------------------------------------------------
     def query(self, pts, cam, feat_geo=None, feat_tex=None, n_views=1, sp_data={}, tx_data={}, view=None,
@@ -226,8 +272,10 @@ class KeypointNeRF(nn.Module):
         assert pts.shape[0] == 1, "batch size 1 only (the reference's bbox test already requires it, src/model.py:1191)"
         feat_geo = self.feat_geo if feat_geo is None else feat_geo
         feat_tex = self.feat_tex if feat_tex is None else feat_tex
-        m = self._bind_scene(cam, feat_geo, feat_tex, sp_data, tx_data["img"], kwargs.get("src_foreground_mask"),
-                             kwargs.get("bounds", torch.zeros(1, 2, 3)))
+        bounds = kwargs.get("bounds")
+        if bounds is None:   # query does not read the bounds; reuse whatever the bound scene has so that it is not re-packed
+            bounds = self._last_bounds if self._last_bounds is not None else torch.zeros(1, 2, 3)
+        m = self._bind_scene(cam, feat_geo, feat_tex, sp_data, tx_data["img"], kwargs.get("src_foreground_mask"), bounds)
         out, valid = m.query(pts[0], view[0], engine=self.engine)
         return out[None], valid[None, :, None]
 
@@ -245,18 +293,45 @@ class KeypointNeRF(nn.Module):
         config = dict(config)
         feat_geo = config.pop("feat_geo", None)
         feat_tex = config.pop("feat_tex", None)
+        shard = config.pop("dist_shard", None)   # extension: (rank, world) -> this rank renders one lattice phase of the frame
         if feat_geo is None:
             feat_geo = net.attach_geo_feat(img_in, return_val=True)
         if feat_tex is None:
             feat_tex = net.attach_tex_feat(img_in, return_val=True)
-        out = KeypointNeRF._render(net, img_in, cam_in, cam_tar, 1, 0, 0, tar_img, feat_geo, feat_tex, sp_data,
-                                   out_device="cpu", **config)
+        if shard is not None and shard[1] > 1:
+            out = KeypointNeRF._render_sharded(net, img_in, cam_in, cam_tar, tar_img, feat_geo, feat_tex, sp_data, shard, **config)
+        else:
+            out = KeypointNeRF._render(net, img_in, cam_in, cam_tar, 1, 0, 0, tar_img, feat_geo, feat_tex, sp_data,
+                                       out_device="cpu", **config)
         ret = {}
         for k, v in out.items():
             if v is None or v.dim() < 3:
                 continue
             ret[k] = v[0] if v.dim() == 4 else v  # (B,C,h,w) -> (C,h,w); (B,h,w) -> (1,h,w) like the reference
+        if "tex_fg_fine" not in ret:
+            # fine=False: the reference's caller reads tex_fg_fine unconditionally (_arrange_nerf_images, src/model.py:428)
+            ret["tex_fg_fine"] = ret["tex_fg"]
         return ret
+
+    @staticmethod
+    def _render_sharded(net, img_in, cam_in, cam_tar, tar_img, feat_geo, feat_tex, sp_data, shard, **config):
+        """One frame over ``world`` ranks (BASELINE config 4): lattice phase per rank, ONE all-gather per plane, host copy."""
+        from . import distributed as D
+        rank, world = shard
+        width = int(cam_tar.get("width", cam_in["width"]))
+        height = int(cam_tar.get("height", cam_in["height"]))
+        fine = config.get("fine", False)
+        m = net._bind_scene(cam_in, feat_geo, feat_tex, sp_data, img_in, config.get("src_foreground_mask"), config["bounds"])
+        res = D.render_frame_lattice_sharded(m, K=cam_tar["K"], RT=cam_tar["RT"], znear=cam_tar.get("znear", cam_in["znear"]),
+                                             zfar=cam_tar.get("zfar", cam_in["zfar"]), width=width, height=height, rank=rank,
+                                             world=world, S_c=config.get("sample_per_ray_c", 64),
+                                             S_f=config.get("sample_per_ray_f", 64), fine=fine, engine=net.engine,
+                                             ert_eps=config.get("ert_eps", 0.0))
+        keys = ["tex_fg", "depth", "alpha"] + (["tex_fg_fine", "depth_fine", "alpha_fine", "sdf"] if fine else [])
+        out = {k: res[k].cpu()[None] for k in keys}
+        if tar_img is not None:
+            out["tar_img"] = tar_img.cpu()
+        return out
 
     # ---- one pass (reference src/model.py:942-1108) ----------------------------------------------
     @staticmethod
@@ -289,9 +364,15 @@ class KeypointNeRF(nn.Module):
         S_f = config.get("sample_per_ray_f", 64)
         fine = config.get("fine", False)
         if not config.get("uniform", False):
-            raise NotImplementedError("uniform=False (stratified jitter) is a training-time option outside this build")
-        if config.get("separate_cf", False) or config.get("rand_noise_std", 0.0) > 0.0 and net.training:
-            raise NotImplementedError("separate_cf / density noise are training-time options outside this build")
+            raise NotImplementedError("uniform=False (stratified jitter of the sample depths, the default of dr_kwargs in "
+                                      "configs/zju.json) is a training-time option outside this build: pass uniform=True, as the "
+                                      "reference's own render/validation/test callers do (src/model.py:463)")
+        if config.get("separate_cf", False):
+            raise NotImplementedError("separate_cf (separate coarse/fine heads) is outside this build")
+        if config.get("rand_noise_std", 0.0) > 0.0:
+            raise NotImplementedError("rand_noise_std > 0 (density noise, dr_kwargs.rand_noise_std of configs/zju.json) is a "
+                                      "training-time option outside this build: the reference's render callers do not pass it "
+                                      "(src/model.py:453-473)")
         width = int(cam_tar.get("width", cam_in["width"]))
         height = int(cam_tar.get("height", cam_in["height"]))
         znear = cam_tar.get("znear", cam_in["znear"])

@@ -98,9 +98,22 @@ class RayMarcher:
             t = _f32c(t)
             return t if t.device == dev else t.to(dev)
 
+        layout = 0
+
+        def prep_map(t, bit):
+            # feature maps that are already stored [V][H][W][C] (channels-last encoder outputs) are taken as they are
+            nonlocal layout
+            t = t.detach()
+            if t.dtype == torch.float32 and t.device == dev and t.dim() == 4 and t.shape[1] > 1 \
+                    and t.is_contiguous(memory_format=torch.channels_last):
+                layout |= bit
+                return t
+            return prep(t)
+
         KRT, extrin = prep(KRT).reshape(-1, 4, 4), prep(extrin).reshape(-1, 4, 4)
         kpt3d, bounds = prep(kpt3d).reshape(-1, 3), prep(bounds).reshape(2, 3)
-        feat64, feat8, feat_tex, img = prep(feat64), prep(feat8), prep(feat_tex), prep(img)
+        feat64, feat8 = prep_map(feat64, L.KPN_NHWC_FEAT64), prep_map(feat8, L.KPN_NHWC_FEAT8)
+        feat_tex, img = prep_map(feat_tex, L.KPN_NHWC_FEATTEX), prep(img)
         V = img.shape[0]
         s = L.KpnScene()
         s.n_views, s.n_kpt = V, kpt3d.shape[0]
@@ -119,13 +132,22 @@ class RayMarcher:
         else:
             s.fg = None
         s.mem = L.KPN_MEM_DEVICE if on_dev else L.KPN_MEM_HOST
+        s.layout = layout
         L.check(self.lib, self.ctx, self.lib.kpn_set_scene(self.ctx, C.byref(s), self._stream()), "kpn_set_scene")
         self._keep = keep
         self.n_views = V
 
     # ---- render --------------------------------------------------------------------------------
+    def reserve(self, max_rays: int, max_samples: int):
+        """Pre-size the workspace so that later renders of at most this size never allocate (``kpn_reserve``)."""
+        L.check(self.lib, self.ctx, self.lib.kpn_reserve(self.ctx, int(max_rays), int(max_samples)), "kpn_reserve")
+
+    def check_health(self):
+        """Raise if a tensor-core kernel's barrier wait gave up since the last check (``kpn_check_health``)."""
+        L.check(self.lib, self.ctx, self.lib.kpn_check_health(self.ctx, self._stream()), "kpn_check_health")
+
     def render(self, *, K, RT, znear, zfar, x0, y0, step, nx, ny, S_c, S_f=0, fine=False, out_device=None,
-               engine=0, z_fine_override=None, debug=False, ert_eps=0.0) -> dict:
+               engine=0, z_fine_override=None, debug=False, ert_eps=0.0, step_y=0) -> dict:
         """One ``kpn_render`` call.  Returns planar tensors on ``out_device`` ('cuda' or 'cpu';
         default: where K lives)."""
         K, RT = _f32c(K).reshape(-1, 4, 4)[0].contiguous(), _f32c(RT).reshape(-1, 4, 4)[0].contiguous()
@@ -136,7 +158,7 @@ class RayMarcher:
         tg = L.KpnTarget()
         tg.K, tg.RT = K.data_ptr(), RT.data_ptr()
         tg.znear, tg.zfar = float(znear), float(zfar)
-        tg.x0, tg.y0, tg.step, tg.nx, tg.ny = int(x0), int(y0), int(step), int(nx), int(ny)
+        tg.x0, tg.y0, tg.step, tg.nx, tg.ny, tg.step_y = int(x0), int(y0), int(step), int(nx), int(ny), int(step_y)
         tg.mem = L.KPN_MEM_DEVICE if K.is_cuda else L.KPN_MEM_HOST
         op = L.KpnOpts()
         op.sample_per_ray_c, op.sample_per_ray_f, op.fine = int(S_c), int(S_f), int(bool(fine))
@@ -172,6 +194,7 @@ class RayMarcher:
         self._keep_call = keep
         if host_out:  # results are host tensors: make them readable on return (reference does .cpu(), src/model.py:929)
             torch.cuda.current_stream(self.device).synchronize()
+            self.check_health()   # the watchdog words travelled with the results: a tripped barrier wait raises here
         return res
 
     def query(self, pts: torch.Tensor, view: torch.Tensor, engine: int = 0):
@@ -194,6 +217,7 @@ class RayMarcher:
         self._keep_call = [pts, view]
         if not on_dev:
             torch.cuda.current_stream(self.device).synchronize()
+            self.check_health()
         return out, valid.bool()
 
     def stats(self) -> dict:
@@ -201,7 +225,7 @@ class RayMarcher:
         L.check(self.lib, self.ctx, self.lib.kpn_get_stats(self.ctx, C.byref(st), self._stream()), "kpn_get_stats")
         return {"samples_total": int(st.samples_total), "samples_valid": int(st.samples_valid),
                 "kernel_launches": int(st.kernel_launches), "shade_launches": int(st.shade_launches),
-                "shade_ms": float(st.shade_ms)}
+                "shade_ms": float(st.shade_ms), "samples_coloured": int(st.samples_coloured), "geo_ms": float(st.geo_ms)}
 
     def set_profiling(self, enable: bool):
         L.check(self.lib, self.ctx, self.lib.kpn_set_profiling(self.ctx, int(bool(enable))), "kpn_set_profiling")

@@ -15,7 +15,7 @@ def build_model(weights: dict, n_kpt: int, device="cuda:0") -> KeypointNeRF:
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
     res = net.load_state_dict(sd, strict=False)
     assert not res.unexpected_keys, res.unexpected_keys
-    missing = [k for k in res.missing_keys if not k.startswith("sp_encoder")]
+    missing = [k for k in res.missing_keys if not k.startswith(("sp_encoder", "geo_encoder", "tex_encoder"))]
     assert not missing, missing
     return net.to(device).eval()
 

@@ -50,6 +50,17 @@ def _worker(rank, world, port, height, width, q):
                                          world=world, S_c=4)
     ok = ok and set(sharded) == {"tex_fg", "alpha"} and torch.equal(sharded["tex_fg"], _fake_render(0, height, width))
     ok = ok and torch.equal(sharded["alpha"], _fake_render(0, height, width)[1])
+
+    class LatticeMarcher:   # the lattice phase (x0, y0, step, step_y) of the same deterministic frame
+        def render(self, *, K, RT, znear, zfar, x0, y0, step, step_y, nx, ny, out_device, **kw):
+            f = _fake_render(0, height, width)[:, y0::step_y, x0::step]
+            assert f.shape[1:] == (ny, nx) and out_device == "cuda"
+            return {"tex_fg": f.contiguous(), "alpha": f[1].contiguous(), "contrib": torch.zeros(ny * nx, 4)}
+
+    lat = D.render_frame_lattice_sharded(LatticeMarcher(), K=None, RT=None, znear=2.0, zfar=5.0, width=width, height=height,
+                                         rank=rank, world=world, S_c=4)
+    ok = ok and set(lat) == {"tex_fg", "alpha"} and torch.equal(lat["tex_fg"], _fake_render(0, height, width))
+    ok = ok and torch.equal(lat["alpha"], _fake_render(0, height, width)[1])
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
@@ -66,6 +77,20 @@ def test_row_shard_all_gather_world2(height):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_lattice_phases_cover_every_pixel_once():
+    for world in (1, 2, 3, 4, 6, 8, 16):
+        sy, sx = D.lattice_shape(world)
+        assert sy * sx == world and sy <= sx
+        img = torch.arange(3 * 24 * 48, dtype=torch.float32).reshape(3, 24, 48)
+        shards = []
+        for r in range(world):
+            y0, x0, a, b = D.lattice_phase(r, world)
+            assert (a, b) == (sy, sx)
+            shards.append(img[:, y0::a, x0::b])
+        assert torch.equal(D.interleave_lattice(torch.stack(shards), world), img)
+        assert torch.equal(D.interleave_lattice(torch.stack([s[0] for s in shards]), world), img[0])
 
 
 def test_row_shard_covers_every_row_once():

@@ -325,16 +325,20 @@ def test_edge_cases():
     r = m.render(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=16, ny=16, S_c=1)
     torch.cuda.synchronize()
     assert torch.isfinite(r["tex_fg"]).all()
-    # two source views: the tensor-core engine does not cover it, the fp32 engine takes over (still CUDA)
+    # two source views: the tensor-core engine does not cover it and says so (no silent 25x cliff); the fp32 engine,
+    # requested explicitly, renders it (still CUDA)
+    from keypointnerf_b200._lib import KpnError
     s2 = syn.make_scene(src_size=64, n_views=2, n_kpt=18)
     a2 = scene_tensors(s2, target, "cuda:0")
     m2 = net._bind_scene(a2["cam"], a2["feat_geo"], a2["feat_tex"], a2["sp_data"], a2["img"], a2["fg"], a2["bounds"])
-    r2 = m2.render(K=a2["cam_tar"]["K"], RT=a2["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=16, ny=16, S_c=8)
+    kw2 = dict(K=a2["cam_tar"]["K"], RT=a2["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=16, ny=16, S_c=8)
+    with pytest.raises(KpnError, match="engine = 1"):
+        m2.render(**kw2)
+    r2 = m2.render(engine=1, **kw2)
     torch.cuda.synchronize()
     ref2 = O.render_pixels(s2, O.fold_weights(weights), target, O.pixel_lattice(16, 16, 1, 0, 0), 8)
     assert np.abs(r2["tex_fg"].cpu().numpy().reshape(3, -1).T - ref2["tex_fg"].numpy()).max() < 1e-4
     # bad arguments fail loudly
-    from keypointnerf_b200._lib import KpnError
     with pytest.raises(KpnError):
         m.render(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=16, ny=16, S_c=0)
     with pytest.raises(KpnError):
@@ -369,6 +373,14 @@ def test_full_frame_properties_at_baseline_size():
     assert torch.equal(frame["tex_fg"][:, y0:y0 + ny], band["tex_fg"]) and torch.equal(frame["alpha"][y0:y0 + ny], band["alpha"])
     whole = D.render_frame_row_sharded(m, width=512, height=512, rank=0, world=1, **kw)
     assert torch.equal(whole["tex_fg"], frame["tex_fg"])
+    # BASELINE config 4's partition: the 8 lattice phases (2 x 4), each rendered on its own as one rank would, interleave to
+    # the frame bit-for-bit
+    phases = []
+    for r in range(8):
+        py, px, sy, sx = D.lattice_phase(r, 8)
+        phases.append(m.render(x0=px, y0=py, step=sx, step_y=sy, nx=512 // sx, ny=512 // sy, **kw)["tex_fg"])
+    assert torch.equal(D.interleave_lattice(torch.stack(phases), 8), frame["tex_fg"])
+    m.check_health()
     al = frame["alpha"]
     assert float(al.min()) >= 0.0 and float(al.max()) <= 1.0 + 1e-5
     assert float(frame["tex_fg"].min()) >= -1e-6 and float(frame["tex_fg"].max()) <= 1.0 + 1e-5
@@ -448,3 +460,59 @@ def test_early_ray_termination(engine):
     # the fine pass resamples from the (slightly different) coarse weights: robust comparison as for the free-running fine pass
     q = float(torch.quantile((ert["tex_fg_fine"] - exact["tex_fg_fine"]).abs().flatten().float().cpu(), 0.99))
     assert q <= 5e-3
+
+
+def test_encoders_feed_the_kernels_in_place():
+    """attach_im_feat path: the channels-last encoders' outputs are gathered from in place (NHWC, no re-layout
+    pass) and give bit-identical images to the same maps passed as ordinary NCHW tensors; the maps are cached per source-image
+    set (the second camera of a sweep does not re-run the encoders), and match the fp32 NCHW encoders to conv round-off."""
+    from keypointnerf_b200 import encoders as E
+    torch.manual_seed(0)
+    scene = syn.make_scene(src_size=256, n_kpt=18, fg_mode="hull")
+    weights = syn.make_weights(18)
+    net = build_model(weights, 18, "cuda:0")
+    target = syn.make_target(size=64, zoom=2.0)
+    a = scene_tensors(scene, target, "cuda:0")
+    cfg = dict(sample_per_ray_c=24, sample_per_ray_f=0, fine=False, uniform=True, src_foreground_mask=a["fg"], bounds=a["bounds"],
+               mask_at_box=None)
+    with torch.no_grad():
+        net.attach_im_feat(a["img"])
+        fg0, ft0 = net.feat_geo, net.feat_tex
+        assert fg0[0].shape == (3, 64, 32, 32) and fg0[1].shape == (3, 8, 128, 128) and ft0.shape == (3, 8, 64, 64)
+        assert E.is_nhwc(fg0[0]) and E.is_nhwc(fg0[1]) and E.is_nhwc(ft0)
+        out_nhwc = net.render_pifu_nerf(net, a["img"], a["cam"], a["cam_tar"], level=1, sp_data=a["sp_data"], **cfg)
+        net.attach_im_feat(a["img"])
+        assert net.feat_geo[0] is fg0[0] and net.feat_tex is ft0, "feature maps of the same source images must be cached"
+        nchw = lambda t: t.contiguous(memory_format=torch.contiguous_format)
+        out_nchw = net.render_pifu_nerf(net, a["img"], a["cam"], a["cam_tar"], level=1, sp_data=a["sp_data"],
+                                        feat_geo=[nchw(fg0[0]), nchw(fg0[1])], feat_tex=nchw(ft0), **cfg)
+    assert torch.equal(out_nhwc["tex_fg"], out_nchw["tex_fg"]) and torch.equal(out_nhwc["alpha"], out_nchw["alpha"])
+    assert torch.equal(out_nhwc["tex_fg_fine"], out_nhwc["tex_fg"])   # fine=False: alias the reference's caller reads
+    assert float(out_nhwc["alpha"].max()) > 0.05
+    # the same encoders in plain NCHW fp32 without TF32: the channels-last run agrees to convolution round-off
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            x = torch.nn.functional.avg_pool2d(a["img"], 2, stride=2) * 2.0 - 1.0
+            ref = net.geo_encoder(x.contiguous())
+            got = net.geo_encoder(x.contiguous(memory_format=torch.channels_last))
+        assert float((ref[0] - got[0]).abs().max()) < 1e-3 * float(ref[0].abs().max())
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_multi_gpu_equals_single_gpu():
+    """BASELINE configs 4 and 5 on 2 GPUs (NCCL): the lattice-sharded frame and the gathered views are bit-identical to the
+    single-GPU renders.  Needs >= 2 devices (skipped on the single-GPU test box; run with `gpurun --gpus 2`)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "tools", "multi_gpu_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    print(p.stdout[-2000:], p.stderr[-2000:])
+    assert p.returncode == 0 and "MULTI_GPU_OK" in p.stdout
