@@ -201,6 +201,10 @@ int kpn_debug_timing(kpn_ctx* ctx, int enable, unsigned long long* out16);
  * {18, 24}: kmap_out[i] = K index input i is multiplied with, *kbias_out = K index of the bias row, *kpad_out = padded K. */
 int kpn_debug_kmap(int stage, int n_kpt, int n_inputs, int* kmap_out, int* kbias_out, int* kpad_out);
 
+/* Debug, instrumented build (-DKPN_STAGE_TIMING, tools/stage_times.py) only: per-stage cycle stamps of one issuer warp of the
+ * geometry kernel; KPN_ERR_UNSUPPORTED in the normal build. */
+int kpn_debug_stage_times(kpn_ctx* ctx, unsigned long long* out, int n_words, int* n_tiles);
+
 /* enable != 0: bracket every shading-kernel launch with CUDA events on its stream (no sync). */
 int kpn_set_profiling(kpn_ctx* ctx, int enable);
 

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkpnerf_b200.so")
+# KPN_LIB selects an alternative build of the same ABI (the instrumented library of tools/stage_times.py)
+LIB_PATH = os.environ.get("KPN_LIB") or os.path.join(_HERE, "lib", "libkpnerf_b200.so")
 
 KPN_OK = 0
 KPN_MEM_DEVICE = 0
@@ -18,7 +19,7 @@ KPN_NUM_LAYERS = 19
 KPN_NHWC_FEAT64, KPN_NHWC_FEAT8, KPN_NHWC_FEATTEX = 1, 2, 4
 
 EXPORTS = ["kpn_abi_version", "kpn_create", "kpn_destroy", "kpn_last_error", "kpn_set_weights", "kpn_set_scene",
-           "kpn_render", "kpn_query", "kpn_get_stats", "kpn_set_profiling", "kpn_selftest_umma", "kpn_selftest_umma2", "kpn_debug_timing", "kpn_debug_kmap", "kpn_check_health", "kpn_reserve"]
+           "kpn_render", "kpn_query", "kpn_get_stats", "kpn_set_profiling", "kpn_selftest_umma", "kpn_selftest_umma2", "kpn_debug_timing", "kpn_debug_kmap", "kpn_check_health", "kpn_reserve", "kpn_debug_stage_times"]
 KPN_ABI_VERSION = 2
 
 c_float_p = C.POINTER(C.c_float)

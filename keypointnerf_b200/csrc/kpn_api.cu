@@ -70,7 +70,10 @@ struct kpn_ctx {
   DevBuf stage[4];             // host-sourced maps before packing
   DevBuf atlas[4];             // f64, f8, ftex, img (channel-last fp32)
   DevBuf atlas_fg;
-  DevBuf ws_z, ws_rgba, ws_list, ws_rayd, ws_raynf, ws_contrib, ws_zfine, ws_out, ws_in, ws_lat, ws_list2, ws_ert;
+  // per-chunk workspace: rays (dir, near/far), per-ray list ranges of up to two segments, the work list, the compact per-sample
+  // records (alpha+sdf, rgb, compositing weight), the fine depths, the colour kernel's latent scratch + work list
+  DevBuf ws_rayd, ws_raynf, ws_rayseg, ws_list, ws_ao, ws_rgb, ws_cw, ws_zfine, ws_lat, ws_list2, ws_ert, ws_contrib;
+  DevBuf ws_out, ws_in;
   unsigned long long launches = 0;
   bool profiling = false;
   unsigned int* h_wd = nullptr;   // pinned host copy of the tensor-core kernels' watchdog words (refreshed by every render/query)
@@ -136,9 +139,9 @@ extern "C" void kpn_destroy(kpn_ctx* c) {
   for (auto& b : c->stage) b.release();
   for (auto& b : c->atlas) b.release();
   c->atlas_fg.release();
-  c->ws_z.release(); c->ws_rgba.release(); c->ws_list.release(); c->ws_rayd.release(); c->ws_raynf.release();
-  c->ws_contrib.release(); c->ws_zfine.release(); c->ws_out.release(); c->ws_in.release();
-  c->ws_lat.release(); c->ws_list2.release(); c->ws_ert.release();
+  for (DevBuf* b : {&c->ws_rayd, &c->ws_raynf, &c->ws_rayseg, &c->ws_list, &c->ws_ao, &c->ws_rgb, &c->ws_cw, &c->ws_zfine, &c->ws_lat,
+                    &c->ws_list2, &c->ws_ert, &c->ws_contrib, &c->ws_out, &c->ws_in})
+    b->release();
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_wd) cudaFreeHost(c->h_wd);
   delete c;
@@ -376,16 +379,14 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
 // ---------------------------------------------------------------------------------------------
 // shading of a batch of samples with the selected engine
 // ---------------------------------------------------------------------------------------------
-static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_mode, int slot, float* out5,
-                       uint8_t* valid_out, int engine, cudaStream_t st, const ErtSegment& ert = ErtSegment{0, 0, nullptr, 0.0f}) {
+// Shades the samples of list[0 .. *counter) (device-side count, at most n) with the selected engine; `so` says where the results go.
+static int shade_batch(kpn_ctx* c, const SampleSrc& src, const int* list, const int* counter, int* counter2, long long n,
+                       int query_mode, const ShadeOut& so, int engine, cudaStream_t st) {
   const bool use_tc = engine != 1;
   if (use_tc && !(c->tc_weights && tc_supported(c->scene_views, c->n_kpt, c->sp_level)))
     KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "the tensor-core engine covers n_views == 3, n_kpt in {18, 24}, sp_level == 3; this scene has "
              "n_views=%d n_kpt=%d sp_level=%d: request engine = 1 (fp32 CUDA-core engine, ~25x slower) explicitly",
              c->scene_views, c->n_kpt, c->sp_level);
-  KPN_CUDA(c, c->ws_list.reserve((size_t)n * sizeof(int)));
-  int* counter = c->d_counters + slot;
-  KPN_CUDA(c, launch_compact(c->d_scene, src, n, query_mode, c->ws_list.as<int>(), counter, out5, valid_out, ert, st));
   cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr;   // start | after the geometry kernel | stop
   if (c->profiling) {
     while (c->ev_used + 3 > c->ev_pool.size()) {
@@ -401,17 +402,15 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, long long n, int query_
     KPN_CUDA(c, c->ws_lat.reserve((size_t)n * 48));
     KPN_CUDA(c, c->ws_list2.reserve((size_t)n * 8));
     KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), c->wlo.as<uint8_t>(), engine == 2 ? 0 : 1, c->n_kpt,
-                                src, c->ws_list.as<int>(), counter, n, query_mode, out5, c->ws_lat.p, c->ws_list2.p,
-                                c->d_counters2 + slot, c->num_sms, em, st));
-    c->launches++;
+                                src, list, counter, n, query_mode, so, c->ws_lat.p, c->ws_list2.p, counter2, c->num_sms, em, st));
+    c->launches += 2;
   }
   else {
-    KPN_CUDA(c, launch_shade_simt(c->d_scene, c->d_wf32, src, c->ws_list.as<int>(), counter, n, query_mode, out5,
-                                  c->num_sms, st));
+    KPN_CUDA(c, launch_shade_simt(c->d_scene, c->d_wf32, src, list, counter, n, query_mode, so, c->num_sms, st));
     if (c->profiling) KPN_CUDA(c, cudaEventRecord(em, st));
+    c->launches++;
   }
   if (c->profiling) KPN_CUDA(c, cudaEventRecord(e1, st));
-  c->launches += 2;
   return KPN_OK;
 }
 
@@ -435,12 +434,14 @@ static int reserve_render(kpn_ctx* c, long long Rc, int Sc, int Smax, bool fine,
   const size_t n = (size_t)Rc * Smax;
   KPN_CUDA(c, c->ws_rayd.reserve((size_t)Rc * 3 * sizeof(float)));
   KPN_CUDA(c, c->ws_raynf.reserve((size_t)Rc * 2 * sizeof(float)));
-  KPN_CUDA(c, c->ws_z.reserve((size_t)Rc * Sc * sizeof(float)));
-  KPN_CUDA(c, c->ws_rgba.reserve(n * 5 * sizeof(float)));
+  KPN_CUDA(c, c->ws_rayseg.reserve((size_t)Rc * 4 * sizeof(int)));   // start | cnt of segment 0, start | cnt of segment 1
   KPN_CUDA(c, c->ws_list.reserve(n * sizeof(int)));
+  KPN_CUDA(c, c->ws_ao.reserve(n * sizeof(float2)));
+  KPN_CUDA(c, c->ws_rgb.reserve(n * 3 * sizeof(float)));
   KPN_CUDA(c, c->ws_lat.reserve(n * 48));
   KPN_CUDA(c, c->ws_list2.reserve(n * 8));
-  if (fine || contrib) KPN_CUDA(c, c->ws_contrib.reserve((size_t)Rc * Sc * sizeof(float)));
+  if (fine || contrib) KPN_CUDA(c, c->ws_cw.reserve((size_t)Rc * Sc * sizeof(float)));
+  if (contrib) KPN_CUDA(c, c->ws_contrib.reserve((size_t)Rc * Sc * sizeof(float)));
   if (fine) KPN_CUDA(c, c->ws_zfine.reserve(n * sizeof(float)));
   if (ert) KPN_CUDA(c, c->ws_ert.reserve((size_t)Rc * sizeof(float)));
   return KPN_OK;
@@ -517,54 +518,78 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
   rc = begin_counters(c, st);
   if (rc != KPN_OK) return rc;
   cudaMemcpyKind okind = host_out ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-  // Shade the S samples of nr rays into ws_rgba.  Early-ray termination (ert_eps > 0, S >= 8): the front half of every ray is
-  // shaded and composited first; rays whose transmittance behind it is < ert_eps skip the back half (their remaining
-  // contribution to any channel is < ert_eps; the reference has no such option, ert_eps = 0 reproduces it exactly).
-  auto march = [&](const SampleSrc& src, int nr, int S, const float* zbuf, int slot) -> int {
+  int* seg = c->ws_rayseg.as<int>();
+  int* list = c->ws_list.as<int>();
+  float2* ao = c->ws_ao.as<float2>();
+  float* rgbw = c->ws_rgb.as<float>();
+  // One pass over nr rays x S samples (zbuf == nullptr: the coarse pass, uniform depths): front (rays + validity + ray-ordered
+  // work list) -> shading -> compositing.  Early-ray termination (ert_eps > 0, S >= 8): the front half of every ray is shaded
+  // and composited first; rays whose transmittance behind it is < ert_eps get no entries for the back half (their remaining
+  // contribution to any channel is < ert_eps; the reference has no such option, ert_eps = 0 reproduces it exactly).  The
+  // back half's entries live in the list range [nr*half, nr*S) and have their own per-ray ranges (segment 1).
+  auto pass = [&](int r0, int nr, int S, const float* zbuf, int slot, float* color, float* depth, float* alpha, float* sdf,
+                  float* cw) -> int {
+    SampleSrc src;
+    memset(&src, 0, sizeof(src));
+    src.mode = 0; src.S = S; src.ray_d = c->ws_rayd.as<float>(); src.z = zbuf; src.ray_nf = c->ws_raynf.as<float>(); src.o = d_o;
     const long long n = (long long)nr * S;
-    if (!ert_on || S < 8) return shade_batch(c, src, n, 0, slot, c->ws_rgba.as<float>(), nullptr, op->engine, st);
+    int* start0 = seg; int* cnt0 = seg + Rc; int* start1 = seg + 2 * Rc; int* cnt1 = seg + 3 * Rc;
+    const bool two = ert_on && S >= 8;
     const int half = S / 2;
-    int r1 = shade_batch(c, src, n, 0, slot, c->ws_rgba.as<float>(), nullptr, op->engine, st, ErtSegment{0, half, nullptr, 0.0f});
-    if (r1 != KPN_OK) return r1;
-    KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), zbuf, 0, nr, S, half, nr, nullptr, nullptr, c->ws_ert.as<float>(), nullptr,
-                                 nullptr, st));
+    ShadeOut so;
+    memset(&so, 0, sizeof(so));
+    so.ao = ao; so.rgb = rgbw;
+    KPN_CUDA(c, launch_front(c->d_scene, c->d_target, r0, nr, S, zbuf, c->ws_rayd.as<float>(), c->ws_raynf.as<float>(), list, 0,
+                             c->d_counters + slot, start0, cnt0, two ? ErtSegment{0, half, nullptr, 0.0f} : ErtSegment{0, 0, nullptr, 0.0f}, st));
     c->launches++;
-    return shade_batch(c, src, n, 0, slot + 1, c->ws_rgba.as<float>(), nullptr, op->engine, st,
-                       ErtSegment{half, S, c->ws_ert.as<float>(), op->ert_eps});
+    so.list_base = 0;
+    int r1 = shade_batch(c, src, list, c->d_counters + slot, c->d_counters2 + slot, two ? (long long)nr * half : n, 0, so, op->engine, st);
+    if (r1 != KPN_OK) return r1;
+    if (two) {
+      KPN_CUDA(c, launch_composite(list, ao, rgbw, start0, cnt0, nullptr, nullptr, zbuf, c->ws_raynf.as<float>(), r0, nr, S, R, nullptr,
+                                   nullptr, nullptr, nullptr, c->ws_ert.as<float>(), nullptr, st));
+      const int base1 = nr * half;
+      KPN_CUDA(c, launch_front(c->d_scene, c->d_target, r0, nr, S, zbuf ? zbuf : nullptr, c->ws_rayd.as<float>(), c->ws_raynf.as<float>(),
+                               list, base1, c->d_counters + slot + 1, start1, cnt1, ErtSegment{half, S, c->ws_ert.as<float>(), op->ert_eps}, st));
+      c->launches += 2;
+      so.list_base = base1;
+      r1 = shade_batch(c, src, list + base1, c->d_counters + slot + 1, c->d_counters2 + slot + 1, n - base1, 0, so, op->engine, st);
+      if (r1 != KPN_OK) return r1;
+    }
+    KPN_CUDA(c, launch_composite(list, ao, rgbw, start0, cnt0, two ? start1 : nullptr, two ? cnt1 : nullptr, zbuf, c->ws_raynf.as<float>(),
+                                 r0, nr, S, R, color, depth, alpha, sdf, nullptr, cw, st));
+    c->launches++;
+    return KPN_OK;
   };
 
   for (long long ch = 0; ch < nchunks; ++ch) {
     const long long r0 = ch * Rc;
     const int nr = (int)((R - r0) < Rc ? (R - r0) : Rc);
-    KPN_CUDA(c, launch_rays(c->d_scene, c->d_target, (int)r0, nr, c->ws_rayd.as<float>(), c->ws_raynf.as<float>(), st));
-    KPN_CUDA(c, launch_coarse_z(c->ws_raynf.as<float>(), nr, Sc, c->ws_z.as<float>(), st));
-    c->launches += 2;
-    SampleSrc src;
-    memset(&src, 0, sizeof(src));
-    src.mode = 0; src.S = Sc; src.ray_d = c->ws_rayd.as<float>(); src.z = c->ws_z.as<float>(); src.o = d_o;
-    rc = march(src, nr, Sc, c->ws_z.as<float>(), (int)(4 * ch));
+    // coarse pass; with early-ray termination its weights must still cover every sample of the ray for the resampling pass:
+    // rays that terminated early simply have zero weight behind the cut
+    rc = pass((int)r0, nr, Sc, nullptr, (int)(4 * ch), dev[0], dev[1], dev[2], nullptr, need_contrib ? c->ws_cw.as<float>() : nullptr);
     if (rc != KPN_OK) return rc;
     c->last_total += (unsigned long long)nr * Sc;
-    KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), c->ws_z.as<float>(), (int)r0, nr, Sc, Sc, R, dev[0], dev[1], dev[2],
-                                 nullptr, need_contrib ? c->ws_contrib.as<float>() : nullptr, st));
-    c->launches++;
-    if (out->contrib)
-      KPN_CUDA(c, cudaMemcpyAsync(out->contrib + r0 * Sc, c->ws_contrib.p, (size_t)nr * Sc * sizeof(float), okind, st));
-    if (op->fine) {
-      if (op->z_fine_override) {
-        KPN_CUDA(c, cudaMemcpyAsync(c->ws_zfine.p, op->z_fine_override + r0 * Smax, (size_t)nr * Smax * sizeof(float),
-                                    in_kind(out->mem), st));
-      } else {
-        KPN_CUDA(c, launch_importance(c->ws_contrib.as<float>(), c->ws_z.as<float>(), nr, Sc, Sf, c->ws_zfine.as<float>(), st));
+    if (need_contrib) {
+      // dense weights (debug output) and / or the resampled + merged depths of the fine pass, one warp per ray
+      const bool two = ert_on && Sc >= 8;
+      float* zout = (op->fine && !op->z_fine_override) ? c->ws_zfine.as<float>() : nullptr;
+      float* cden = out->contrib ? c->ws_contrib.as<float>() : nullptr;
+      if (zout || cden) {
+        KPN_CUDA(c, launch_resample(list, c->ws_cw.as<float>(), seg, seg + Rc, two ? seg + 2 * Rc : nullptr, two ? seg + 3 * Rc : nullptr,
+                                    c->ws_raynf.as<float>(), nr, Sc, zout ? Sf : 0, zout, cden, st));
         c->launches++;
       }
-      src.S = Smax; src.z = c->ws_zfine.as<float>();
-      rc = march(src, nr, Smax, c->ws_zfine.as<float>(), (int)(4 * ch + 2));
+      if (out->contrib)
+        KPN_CUDA(c, cudaMemcpyAsync(out->contrib + r0 * Sc, c->ws_contrib.p, (size_t)nr * Sc * sizeof(float), okind, st));
+    }
+    if (op->fine) {
+      if (op->z_fine_override)
+        KPN_CUDA(c, cudaMemcpyAsync(c->ws_zfine.p, op->z_fine_override + r0 * Smax, (size_t)nr * Smax * sizeof(float),
+                                    in_kind(out->mem), st));
+      rc = pass((int)r0, nr, Smax, c->ws_zfine.as<float>(), (int)(4 * ch + 2), dev[3], dev[4], dev[5], dev[6], nullptr);
       if (rc != KPN_OK) return rc;
       c->last_total += (unsigned long long)nr * Smax;
-      KPN_CUDA(c, launch_composite(c->ws_rgba.as<float>(), c->ws_zfine.as<float>(), (int)r0, nr, Smax, Smax, R, dev[3], dev[4],
-                                   dev[5], dev[6], nullptr, st));
-      c->launches++;
       if (out->z_fine)
         KPN_CUDA(c, cudaMemcpyAsync(out->z_fine + r0 * Smax, c->ws_zfine.p, (size_t)nr * Smax * sizeof(float), okind, st));
     }
@@ -611,7 +636,13 @@ extern "C" int kpn_query(kpn_ctx* c, const float* pts, const float* view, int n,
     SampleSrc src;
     memset(&src, 0, sizeof(src));
     src.mode = 1; src.pts = dp + 3 * off; src.view = dv + 3 * off;
-    rc = shade_batch(c, src, m, 1, (int)ch, dout + 5 * off, dvalid + off, op ? op->engine : 0, st);
+    KPN_CUDA(c, c->ws_list.reserve((size_t)m * sizeof(int)));
+    KPN_CUDA(c, launch_compact(c->d_scene, src, m, c->ws_list.as<int>(), c->d_counters + ch, dout + 5 * off, dvalid + off, st));
+    c->launches++;
+    ShadeOut so;
+    memset(&so, 0, sizeof(so));
+    so.out5 = dout + 5 * off;
+    rc = shade_batch(c, src, c->ws_list.as<int>(), c->d_counters + ch, c->d_counters2 + ch, m, 1, so, op ? op->engine : 0, st);
     if (rc != KPN_OK) return rc;
   }
   c->counters_used = (int)nchunks;
@@ -674,6 +705,17 @@ extern "C" int kpn_debug_kmap(int stage, int n_kpt, int n_inputs, int* kmap_out,
   for (int i = 0; i < n_inputs; ++i) kmap_out[i] = tc_kmap(stage, n_kpt, i);
   if (kbias_out) *kbias_out = tc_kbias(stage, n_kpt);
   if (kpad_out) *kpad_out = make_tc_plan(n_kpt).st[stage].Kp;
+  return KPN_OK;
+}
+
+// Debug, instrumented build (-DKPN_STAGE_TIMING) only: cycle stamps of one issuer warp of the geometry kernel (layout in
+// kpn_shade_tc.cu); out receives up to n_words values, *n_tiles the tiles recorded since the last call.
+extern "C" int kpn_debug_stage_times(kpn_ctx* c, unsigned long long* out, int n_words, int* n_tiles) {
+  if (!c || !out || !n_tiles) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  cudaError_t e = tc_stage_times(out, n_words, n_tiles);
+  if (e == cudaErrorNotSupported) KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "library was not built with -DKPN_STAGE_TIMING");
+  KPN_CUDA(c, e);
   return KPN_OK;
 }
 

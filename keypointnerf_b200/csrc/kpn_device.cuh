@@ -13,11 +13,25 @@ __device__ __forceinline__ float softplus100(float x) {
 __device__ __forceinline__ float elu1(float x) { return x > 0.0f ? x : expm1f(x); }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// torch.linspace(0, 1, S) in fp32: symmetric evaluation from both ends (reference src/model.py:1045).
+__device__ __forceinline__ float linspace01(int i, int S) {
+  if (S <= 1) return 0.0f;
+  float step = 1.0f / (float)(S - 1);
+  return i < S / 2 ? step * (float)i : 1.0f - step * (float)(S - 1 - i);
+}
+// depth of coarse sample s of a ray: z = near + (far - near) * linspace(0,1,S)[s]  (reference src/model.py:1045-1055)
+__device__ __forceinline__ float coarse_depth(float n_r, float f_r, int s, int S) { return n_r + (f_r - n_r) * linspace01(s, S); }
+
+__device__ __forceinline__ float sample_depth(const SampleSrc& src, long long id, long long r) {
+  if (src.z) return src.z[id];
+  return coarse_depth(src.ray_nf[2 * r], src.ray_nf[2 * r + 1], (int)(id - r * src.S), src.S);
+}
+
 // ---- sample fetch -----------------------------------------------------------------------------
 __device__ __forceinline__ void fetch_sample(const SampleSrc& src, long long id, float p[3], float d[3]) {
   if (src.mode == 0) {
     long long r = id / src.S;
-    float z = src.z[id];
+    float z = sample_depth(src, id, r);
     d[0] = src.ray_d[3 * r + 0]; d[1] = src.ray_d[3 * r + 1]; d[2] = src.ray_d[3 * r + 2];
     // eval_pts = cam_pos + cam_rays * z  (reference src/model.py:1057)
     p[0] = src.o[0] + d[0] * z; p[1] = src.o[1] + d[1] * z; p[2] = src.o[2] + d[2] * z;

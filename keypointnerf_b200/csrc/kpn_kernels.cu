@@ -3,12 +3,12 @@
 // Stages (reference src/model.py:1018-1096 for the eval branch of batch_render_pifu_nerf):
 //   pack_nhwc      feature maps NCHW -> channel-last atlases (once per scene)
 //   prep_*         derived camera constants on device (no host sync)
-//   rays           pixel lattice -> ray direction, near/far incl. bbox clip
-//   coarse_z       uniform depths
-//   compact        per-sample validity (frustum + foreground in every view) -> compacted work list
+//   front          one kernel per pass: pixel lattice -> ray (direction, near/far incl. bbox clip), depths, per-sample validity
+//                  (frustum + foreground in every view), ray-ordered compacted work list
+//   compact        the same validity test + compaction for explicit points (KeypointNeRF.query)
 //   shade_simt     per-sample gather + keypoint encoding + MLPs for tiles of 64 valid samples
-//   composite      alpha compositing along the ray
-//   importance     inverse-CDF resampling + merge with the coarse depths
+//   composite      alpha compositing along the ray over the compact per-sample records
+//   resample       inverse-CDF resampling + merge with the coarse depths (warp per ray)
 #include <atomic>
 #include "kpn_device.cuh"
 #include "kpn_launch.h"
@@ -132,66 +132,108 @@ __device__ __forceinline__ void ray_for_pixel(const DevScene& sc, const DevTarge
   if (hit && tf < f_r) f_r = tf;
 }
 
-__global__ void rays_kernel(const DevScene* __restrict__ sc, const DevTarget* __restrict__ tg, int r0, int nr,
-                            float* __restrict__ ray_d, float* __restrict__ ray_nf) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nr) return;
-  int r = r0 + i;
-  int ix = r % tg->nx, iy = r / tg->nx;
-  float px = (float)(tg->x0 + tg->step * ix), py = (float)(tg->y0 + tg->step_y * iy);
-  float d[3], n, f;
-  ray_for_pixel(*sc, *tg, px, py, d, n, f);
-  ray_d[3 * i + 0] = d[0]; ray_d[3 * i + 1] = d[1]; ray_d[3 * i + 2] = d[2];
-  ray_nf[2 * i + 0] = n; ray_nf[2 * i + 1] = f;
-}
+// ------------------------------------------------------------------------------------------------
+// front end of a render pass: rays + depths + validity + ray-ordered compaction in ONE kernel
+// ------------------------------------------------------------------------------------------------
+// One warp per ray, 8 rays per block iteration.  Coarse pass (zbuf == nullptr): the warp derives the ray (direction, near/far
+// incl. the bbox clip) and stores it; its depths are the uniform ones and are never stored (every consumer recomputes them
+// with coarse_depth()).  Fine pass: the ray is re-read and the depths come from zbuf (R, S).  Lane l tests samples l, l+32, ..
+// (3 projections + frustum + foreground lookups, reference src/model.py:713-739); the ballots give the ray's valid samples in
+// order.  The 8 rays of a block iteration reserve ONE contiguous range of the work list with one atomicAdd; inside it the
+// entries are ordered by (ray, sample), so that ray r owns list[ray_start[r] .. +ray_cnt[r]) -- the compositing pass walks
+// exactly that range, and nothing is ever written for the invalid samples.
+// Early-ray termination (ert.s_hi > 0): only samples s_lo <= s < s_hi are looked at; a ray whose accumulated alpha of the
+// earlier segment leaves a transmittance < ert.eps contributes no entries (what it could still add is < eps per channel).
+constexpr int FRONT_WARPS = 8;
+constexpr int FRONT_MAXW = 40;   // ballot words per ray: up to 1280 samples (256 coarse + 1024 fine)
 
-__device__ __forceinline__ float linspace01(int i, int S) {
-  // torch.linspace(0, 1, S) in fp32: symmetric evaluation from both ends.
-  if (S <= 1) return 0.0f;
-  float step = 1.0f / (float)(S - 1);
-  return i < S / 2 ? step * (float)i : 1.0f - step * (float)(S - 1 - i);
-}
-
-__global__ void coarse_z_kernel(const float* __restrict__ ray_nf, int nr, int S, float* __restrict__ z) {
-  long long n = (long long)nr * S;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int r = (int)(i / S), s = (int)(i % S);
-    float a = ray_nf[2 * r], b = ray_nf[2 * r + 1];
-    z[i] = a + (b - a) * linspace01(s, S);  // reference src/model.py:1045-1055
+__global__ void __launch_bounds__(FRONT_WARPS * 32)
+front_kernel(const DevScene* __restrict__ scp, const DevTarget* __restrict__ tgp, int r0, int nr, int S,
+             const float* __restrict__ zbuf, float* __restrict__ ray_d, float* __restrict__ ray_nf,
+             int* __restrict__ list, int list_base, int* __restrict__ counter, int* __restrict__ ray_start,
+             int* __restrict__ ray_cnt, ErtSegment ert) {
+  const DevScene& sc = *scp;
+  __shared__ unsigned s_mask[FRONT_WARPS][FRONT_MAXW];
+  __shared__ int s_cnt[FRONT_WARPS];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nwords = (S + 31) >> 5;
+  const int s_lo = ert.s_hi > 0 ? ert.s_lo : 0, s_hi = ert.s_hi > 0 ? ert.s_hi : S;
+  for (int base = blockIdx.x * FRONT_WARPS; base < nr; base += gridDim.x * FRONT_WARPS) {   // block-uniform trip count
+    const int i = base + wid;
+    int cnt = 0;
+    if (i < nr) {
+      float d[3], n_r, f_r;
+      if (zbuf == nullptr) {
+        const DevTarget& tg = *tgp;
+        const int r = r0 + i;
+        const int ix = r % tg.nx, iy = r / tg.nx;
+        ray_for_pixel(sc, tg, (float)(tg.x0 + tg.step * ix), (float)(tg.y0 + tg.step_y * iy), d, n_r, f_r);
+        if (lane == 0) {
+          ray_d[3 * i + 0] = d[0]; ray_d[3 * i + 1] = d[1]; ray_d[3 * i + 2] = d[2];
+          ray_nf[2 * i + 0] = n_r; ray_nf[2 * i + 1] = f_r;
+        }
+      } else {
+        d[0] = ray_d[3 * i + 0]; d[1] = ray_d[3 * i + 1]; d[2] = ray_d[3 * i + 2];
+        n_r = 0.0f; f_r = 0.0f;
+      }
+      const float o0 = tgp->o[0], o1 = tgp->o[1], o2 = tgp->o[2];
+      const bool dead = ert.ray_alpha != nullptr && 1.0f - ert.ray_alpha[i] < ert.eps;   // ray already opaque
+      for (int w = 0; w < nwords; ++w) {
+        const int s = 32 * w + lane;
+        bool ok = false;
+        if (s < S && s >= s_lo && s < s_hi && !dead) {
+          const float z = zbuf ? zbuf[(long long)i * S + s] : coarse_depth(n_r, f_r, s, S);
+          const float p[3] = {o0 + d[0] * z, o1 + d[1] * z, o2 + d[2] * z};   // reference src/model.py:1057
+          Proj q[MAXV];
+          ok = sample_valid(sc, p, q);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_mask[wid][w] = m;
+        cnt += __popc(m);
+      }
+    }
+    if (lane == 0) s_cnt[wid] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < FRONT_WARPS; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    if (i < nr) {
+      int pos = list_base + s_base + s_cnt[wid];
+      if (lane == 0) { ray_start[i] = pos; ray_cnt[i] = cnt; }
+      for (int w = 0; w < nwords; ++w) {
+        const unsigned m = s_mask[wid][w];
+        if ((m >> lane) & 1u) list[pos + __popc(m & ((1u << lane) - 1u))] = i * S + 32 * w + lane;
+        pos += __popc(m);
+      }
+    }
+    __syncthreads();   // s_cnt / s_base / s_mask are rewritten by the next iteration
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// validity + compaction
+// validity + compaction of explicit points (KeypointNeRF.query)
 // ------------------------------------------------------------------------------------------------
-// Early-ray termination (ert.eps > 0, ray mode): only the samples s of a ray with ert.s_lo <= s < ert.s_hi are looked at (the
-// others keep what an earlier segment wrote), and a ray whose transmittance behind the earlier segments, 1 - ert.ray_alpha[ray],
-// is below ert.eps gets alpha = 0 entries instead of being shaded: what it could still add to the pixel is < eps per channel.
-__global__ void compact_kernel(const DevScene* __restrict__ sc, SampleSrc src, long long n, int query_mode,
-                               int* __restrict__ list, int* __restrict__ counter, float* __restrict__ out5,
-                               uint8_t* __restrict__ valid_out, ErtSegment ert) {
+__global__ void compact_kernel(const DevScene* __restrict__ sc, SampleSrc src, long long n, int* __restrict__ list,
+                               int* __restrict__ counter, float* __restrict__ out5, uint8_t* __restrict__ valid_out) {
   const DevScene& S = *sc;
   __shared__ int s_cnt[8];
   __shared__ int s_base;
   for (long long base = (blockIdx.x * (long long)blockDim.x) ; base < n; base += (long long)gridDim.x * blockDim.x) {   // block-uniform trip count
     long long i = base + threadIdx.x;
     bool ok = false;
-    bool in_seg = i < n;
-    if (in_seg && ert.s_hi > 0) {
-      const int sidx = (int)(i % src.S);
-      in_seg = sidx >= ert.s_lo && sidx < ert.s_hi;
-    }
-    if (in_seg) {
+    if (i < n) {
       float p[3], d[3];
       Proj q[MAXV];
       fetch_sample(src, i, p, d);
       ok = sample_valid(S, p, q);
-      if (ok && ert.ray_alpha != nullptr && 1.0f - ert.ray_alpha[i / src.S] < ert.eps) ok = false;   // ray already opaque
-      if (!ok) {
+      if (!ok) {   // rows with valid == 0 carry zeros (the reference multiplies them by a zero mask downstream)
         float* o = out5 + 5 * i;
-        if (query_mode) { o[0] = 0.f; o[1] = 0.f; }
-        else { o[0] = 0.f; o[1] = S.sdf_invalid; }  // alpha = 0, sdf = 0.1/nml_scale (src/model.py:982,996)
-        o[2] = 0.f; o[3] = 0.f; o[4] = 0.f;
+        o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; o[3] = 0.f; o[4] = 0.f;
       }
       if (valid_out) valid_out[i] = ok ? 1 : 0;
     }
@@ -310,8 +352,7 @@ constexpr size_t SHADE_SMEM_BYTES = SHADE_SMEM_FLOATS * sizeof(float);
 
 __global__ void __launch_bounds__(NT, 1)
 shade_simt_kernel(const DevScene* __restrict__ scp, const DevWeightsF32* __restrict__ Wp, SampleSrc src,
-                  const int* __restrict__ list, const int* __restrict__ count_ptr, int query_mode,
-                  float* __restrict__ out5) {
+                  const int* __restrict__ list, const int* __restrict__ count_ptr, int query_mode, ShadeOut so) {
   extern __shared__ float4 smem4[];
   float* sm = reinterpret_cast<float*>(smem4);
   ShadeSmem s;
@@ -538,54 +579,75 @@ shade_simt_kernel(const DevScene* __restrict__ scp, const DevWeightsF32* __restr
         for (int c = 0; c < 3; ++c) rgb[c] += e * s.RGB[(v * TS + t) * 4 + c];
       }
       float g0 = s.Geo[t * 2], rad = s.Geo[t * 2 + 1];
-      float* o = out5 + 5ll * s.Id[t];
-      if (query_mode) { o[0] = g0; o[1] = rad; }
-      else { o[0] = fmaxf(rad, 0.0f); o[1] = g0; }
-      o[2] = rgb[0] / den; o[3] = rgb[1] / den; o[4] = rgb[2] / den;
+      if (query_mode) {
+        float* o = so.out5 + 5ll * s.Id[t];
+        o[0] = g0; o[1] = rad; o[2] = rgb[0] / den; o[3] = rgb[1] / den; o[4] = rgb[2] / den;
+      } else {   // eval_func (reference src/model.py:978-997): alpha = relu(rad), compact record at the sample's list position
+        const long long pos = (long long)so.list_base + base + t;
+        so.ao[pos] = make_float2(fmaxf(rad, 0.0f), g0);
+        float* o = so.rgb + 3 * pos;
+        o[0] = rgb[0] / den; o[1] = rgb[1] / den; o[2] = rgb[2] / den;
+      }
     }
     __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// compositing (reference src/model.py:1150-1176)
+// compositing (reference src/model.py:1150-1176) over the compact per-ray records
 // ------------------------------------------------------------------------------------------------
-// rgba (nr,S,5) = [alpha, sdf, r, g, b]; z (nr,S).  Planar outputs indexed by global ray r0+i.
-// One WARP per ray: lane l takes samples l, l+32, ... (coalesced reads), the transmittance T_k = prod_{j<k} (1 - a_j) is an
-// exclusive product scan across the lanes carried from one group of 32 samples to the next, the ray sums are warp reductions.
+// One WARP per ray walks the ray's range(s) of the work list in sample order: lane l takes entries l, l+32, ... (coalesced),
+// the transmittance T_k = prod_{j<k} (1 - a_j) is an exclusive product scan across the lanes carried from one group of 32
+// entries to the next (invalid samples have a = 0, i.e. a factor of exactly 1, and are simply not there), the ray sums are
+// warp reductions.  Depths: zbuf (fine pass) or recomputed uniform depths (coarse pass).  dist of the ray's last sample is
+// 1e10 (reference src/model.py:1166).  Optional outputs: cw[e] = compositing weight of list entry e (input of the
+// resampling pass), ray_alpha = accumulated alpha of the segments walked (early-ray termination).
+struct RaySeg { const int* start; const int* cnt; };
+
 __global__ void __launch_bounds__(128)
-composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, int r0, int nr, int S, int S_eval,
-                 long long plane, float* __restrict__ color, float* __restrict__ depth,
-                 float* __restrict__ alpha, float* __restrict__ sdf, float* __restrict__ contrib) {
+composite_kernel(const int* __restrict__ list, const float2* __restrict__ ao, const float* __restrict__ rgb, RaySeg seg0,
+                 RaySeg seg1, int nseg, const float* __restrict__ zbuf, const float* __restrict__ ray_nf, int r0, int nr, int S,
+                 long long plane, float* __restrict__ color, float* __restrict__ depth, float* __restrict__ alpha,
+                 float* __restrict__ sdf, float* __restrict__ ray_alpha, float* __restrict__ cw) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nr; i += gridDim.x * wpb) {
-    const float* q = rgba + (long long)i * S * 5;
-    const float* zz = z + (long long)i * S;
-    float Tc = 1.0f;   // transmittance in front of this group of 32 samples
+    const float* zz = zbuf ? zbuf + (long long)i * S : nullptr;
+    const float n_r = zbuf ? 0.0f : ray_nf[2 * i], f_r = zbuf ? 0.0f : ray_nf[2 * i + 1];
+    float Tc = 1.0f;   // transmittance in front of this group of 32 entries
     float acc = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, cd = 0.0f, cs = 0.0f;
-    for (int k0 = 0; k0 < S_eval; k0 += 32) {   // S_eval < S: composite of the first S_eval samples only (ERT segment)
-      const int k = k0 + lane;
-      float a = 0.0f, zk = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f, q4 = 0.0f;
-      if (k < S_eval) {
-        zk = zz[k];
-        const float dist = k + 1 < S ? zz[k + 1] - zk : 1e10f;
-        a = 1.0f - expf(-q[5 * k] * dist);
-        q1 = q[5 * k + 1]; q2 = q[5 * k + 2]; q3 = q[5 * k + 3]; q4 = q[5 * k + 4];
-      }
-      float p = 1.0f - a;   // inclusive product scan of (1 - a)
+    for (int sg = 0; sg < nseg; ++sg) {
+      const RaySeg& sgm = sg == 0 ? seg0 : seg1;
+      const int start = sgm.start[i], cnt = sgm.cnt[i];
+      for (int e0 = 0; e0 < cnt; e0 += 32) {
+        const int e = start + e0 + lane;
+        const bool live = e0 + lane < cnt;
+        float a = 0.0f, zk = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f, q4 = 0.0f;
+        if (live) {
+          const int k = list[e] - i * S;
+          const float2 as = ao[e];
+          float znext;
+          if (zz) { zk = zz[k]; znext = k + 1 < S ? zz[k + 1] : 0.0f; }
+          else { zk = coarse_depth(n_r, f_r, k, S); znext = k + 1 < S ? coarse_depth(n_r, f_r, k + 1, S) : 0.0f; }
+          const float dist = k + 1 < S ? znext - zk : 1e10f;
+          a = 1.0f - expf(-as.x * dist);
+          q1 = as.y;
+          if (as.x > 0.0f) { q2 = rgb[3ll * e]; q3 = rgb[3ll * e + 1]; q4 = rgb[3ll * e + 2]; }   // colour exists iff alpha > 0
+        }
+        float p = 1.0f - a;   // inclusive product scan of (1 - a)
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float t = __shfl_up_sync(0xffffffffu, p, d);
-        if (lane >= d) p *= t;
-      }
-      float ex = __shfl_up_sync(0xffffffffu, p, 1);
-      if (lane == 0) ex = 1.0f;
-      const float c = a * (Tc * ex);
-      Tc *= __shfl_sync(0xffffffffu, p, 31);
-      if (k < S_eval) {
-        acc += c; cr += c * q2; cg += c * q3; cb += c * q4; cd += c * zk; cs += c * q1;
-        if (contrib) contrib[(long long)i * S + k] = c;
+        for (int d = 1; d < 32; d <<= 1) {
+          const float t = __shfl_up_sync(0xffffffffu, p, d);
+          if (lane >= d) p *= t;
+        }
+        float ex = __shfl_up_sync(0xffffffffu, p, 1);
+        if (lane == 0) ex = 1.0f;
+        const float c = a * (Tc * ex);
+        Tc *= __shfl_sync(0xffffffffu, p, 31);
+        if (live) {
+          acc += c; cr += c * q2; cg += c * q3; cb += c * q4; cd += c * zk; cs += c * q1;
+          if (cw) cw[e] = c;
+        }
       }
     }
 #pragma unroll
@@ -599,6 +661,7 @@ composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, in
       if (alpha) alpha[r] = acc;
       if (depth) depth[r] = cd / (acc + 1e-8f);
       if (sdf) sdf[r] = cs / (acc + 1e-8f);
+      if (ray_alpha) ray_alpha[i] = acc;
     }
   }
 }
@@ -606,42 +669,93 @@ composite_kernel(const float* __restrict__ rgba, const float* __restrict__ z, in
 // ------------------------------------------------------------------------------------------------
 // hierarchical resampling (reference src/model.py:1110-1148, 1072-1076), uniform=True
 // ------------------------------------------------------------------------------------------------
-constexpr int MAX_SC = 256;
+// One WARP per ray, everything in shared memory: the ray's compositing weights are scattered from the compact records into a
+// dense array (invalid samples: 0), pdf = (contrib[1:-1] + 1e-5) / sum, cdf by a warp scan, the S_f inverse-CDF samples
+// (searchsorted right=True by binary search, the reference's clamp / den<1e-5 rules), then z_all = sort(cat[z, z_fine]) as a
+// merge by rank (both sequences are monotone; coarse samples come first on ties).  Optional: the dense weights (debug output).
+constexpr int MAX_SC = 256, MAX_SF = 1024, RES_WARPS = 4;
 
-__global__ void importance_kernel(const float* __restrict__ contrib, const float* __restrict__ z, int nr, int Sc, int Sf,
-                                  float* __restrict__ zout) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nr) return;
-  const float* c = contrib + (long long)i * Sc;
-  const float* zz = z + (long long)i * Sc;
-  float* out = zout + (long long)i * (Sc + Sf);
-  const int nb = Sc - 2;   // pdf bins = contrib[1:-1]
-  const int nc = Sc - 1;   // cdf entries == z_mid entries
-  float cdf[MAX_SC];
-  float sum = 0.0f;
-  for (int k = 0; k < nb; ++k) sum += c[k + 1] + 1e-5f;
-  cdf[0] = 0.0f;
-  float run = 0.0f;
-  for (int k = 0; k < nb; ++k) { run += (c[k + 1] + 1e-5f) / sum; cdf[k + 1] = run; }
-  // fine depths are written after the coarse ones, then merged
-  int idx = 0;  // number of cdf entries <= u (searchsorted right=True); u is increasing so idx only grows
-  for (int j = 0; j < Sf; ++j) {
-    float u = linspace01(j, Sf);
-    while (idx < nc && cdf[idx] <= u) ++idx;
-    int lo = max(idx - 1, 0), hi = min(idx, nc - 1);
-    float clo = cdf[lo], chi = cdf[hi];
-    float zlo = 0.5f * (zz[lo + 1] + zz[lo]), zhi = 0.5f * (zz[hi + 1] + zz[hi]);
-    float den = chi - clo;
-    if (den < 1e-5f) den = 1.0f;
-    out[Sc + j] = zlo + ((u - clo) / den) * (zhi - zlo);
-  }
-  for (int k = 0; k < Sc; ++k) out[k] = zz[k];
-  // sort(cat[z, z_fine]): insertion sort (both halves are already ordered, so this is a merge)
-  for (int a = Sc; a < Sc + Sf; ++a) {
-    float val = out[a];
-    int b = a - 1;
-    while (b >= 0 && out[b] > val) { out[b + 1] = out[b]; --b; }
-    out[b + 1] = val;
+__device__ __forceinline__ int count_le(const float* a, int n, float x, bool rev) {   // # of a[i] <= x, a ascending (rev: descending storage)
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[rev ? n - 1 - mid : mid] <= x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int count_lt(const float* a, int n, float x, bool rev) {
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[rev ? n - 1 - mid : mid] < x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(RES_WARPS * 32)
+resample_kernel(const int* __restrict__ list, const float* __restrict__ cw, RaySeg seg0, RaySeg seg1, int nseg,
+                const float* __restrict__ ray_nf, int nr, int Sc, int Sf, float* __restrict__ zout,
+                float* __restrict__ contrib_out) {
+  extern __shared__ float rsm[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int per_warp = 4 * Sc + 2 * Sf;   // cd | cdf | zc | zf | zo
+  float* cd = rsm + wid * per_warp;   // dense weights [Sc]
+  float* cdf = cd + Sc;               // [Sc - 1]
+  float* zc = cdf + Sc;               // coarse depths [Sc]
+  float* zf = zc + Sc;                // fine depths [Sf]
+  float* zo = zf + Sf;                // merged [Sc + Sf]
+  const unsigned FULLM = 0xffffffffu;
+  for (int i = blockIdx.x * RES_WARPS + wid; i < nr; i += gridDim.x * RES_WARPS) {
+    const float n_r = ray_nf[2 * i], f_r = ray_nf[2 * i + 1];
+    for (int k = lane; k < Sc; k += 32) { cd[k] = 0.0f; zc[k] = coarse_depth(n_r, f_r, k, Sc); }
+    __syncwarp();
+    for (int sg = 0; sg < nseg; ++sg) {
+      const RaySeg& sgm = sg == 0 ? seg0 : seg1;
+      const int start = sgm.start[i], cnt = sgm.cnt[i];
+      for (int e = lane; e < cnt; e += 32) cd[list[start + e] - i * Sc] = cw[start + e];
+    }
+    __syncwarp();
+    if (contrib_out) for (int k = lane; k < Sc; k += 32) contrib_out[(long long)i * Sc + k] = cd[k];
+    if (Sf > 0) {
+      const int nb = Sc - 2;   // pdf bins = contrib[1:-1]
+      const int nc = Sc - 1;   // cdf entries == z_mid entries
+      float sum = 0.0f;
+      for (int k = lane; k < nb; k += 32) sum += cd[k + 1] + 1e-5f;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(FULLM, sum, d);
+      float carry = 0.0f;
+      if (lane == 0) cdf[0] = 0.0f;
+      for (int k0 = 0; k0 < nb; k0 += 32) {
+        const int k = k0 + lane;
+        float v = k < nb ? (cd[k + 1] + 1e-5f) / sum : 0.0f;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float t = __shfl_up_sync(FULLM, v, d);
+          if (lane >= d) v += t;
+        }
+        if (k < nb) cdf[k + 1] = carry + v;
+        carry += __shfl_sync(FULLM, v, 31);
+      }
+      __syncwarp();
+      for (int j = lane; j < Sf; j += 32) {
+        const float u = linspace01(j, Sf);
+        const int idx = count_le(cdf, nc, u, false);   // searchsorted(cdf, u, right=True)
+        const int lo = max(idx - 1, 0), hi = min(idx, nc - 1);
+        const float clo = cdf[lo], chi = cdf[hi];
+        const float zlo = 0.5f * (zc[lo + 1] + zc[lo]), zhi = 0.5f * (zc[hi + 1] + zc[hi]);
+        float den = chi - clo;
+        if (den < 1e-5f) den = 1.0f;
+        zf[j] = zlo + ((u - clo) / den) * (zhi - zlo);
+      }
+      __syncwarp();
+      // merge by rank; near > far (depths running backwards, as the reference allows) flips both sequences
+      const bool rev = f_r < n_r;
+      for (int t = lane; t < Sc; t += 32) {
+        const int tt = rev ? Sc - 1 - t : t;
+        zo[t + count_lt(zf, Sf, zc[tt], rev)] = zc[tt];
+      }
+      for (int j = lane; j < Sf; j += 32) {
+        const int jj = rev ? Sf - 1 - j : j;
+        zo[j + count_le(zc, Sc, zf[jj], rev)] = zf[jj];
+      }
+      __syncwarp();
+      for (int k = lane; k < Sc + Sf; k += 32) zout[(long long)i * (Sc + Sf) + k] = zo[k];
+    }
+    __syncwarp();
   }
 }
 
@@ -668,21 +782,20 @@ cudaError_t launch_prep_target(const RawTarget* raw, DevTarget* tg, cudaStream_t
   prep_target_kernel<<<1, 32, 0, st>>>(raw, tg);
   return cudaGetLastError();
 }
-cudaError_t launch_rays(const DevScene* sc, const DevTarget* tg, int r0, int nr, float* ray_d, float* ray_nf, cudaStream_t st) {
-  rays_kernel<<<grid_for(nr, 128, 1 << 30), 128, 0, st>>>(sc, tg, r0, nr, ray_d, ray_nf);
+cudaError_t launch_front(const DevScene* sc, const DevTarget* tg, int r0, int nr, int S, const float* zbuf, float* ray_d,
+                         float* ray_nf, int* list, int list_base, int* counter, int* ray_start, int* ray_cnt, const ErtSegment& ert,
+                         cudaStream_t st) {
+  front_kernel<<<grid_for(nr, FRONT_WARPS, 148 * 8), FRONT_WARPS * 32, 0, st>>>(sc, tg, r0, nr, S, zbuf, ray_d, ray_nf, list, list_base,
+                                                                            counter, ray_start, ray_cnt, ert);
   return cudaGetLastError();
 }
-cudaError_t launch_coarse_z(const float* ray_nf, int nr, int S, float* z, cudaStream_t st) {
-  coarse_z_kernel<<<grid_for((long long)nr * S, 256, 148 * 16), 256, 0, st>>>(ray_nf, nr, S, z);
-  return cudaGetLastError();
-}
-cudaError_t launch_compact(const DevScene* sc, const SampleSrc& src, long long n, int query_mode, int* list, int* counter,
-                           float* out5, uint8_t* valid_out, const ErtSegment& ert, cudaStream_t st) {
-  compact_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(sc, src, n, query_mode, list, counter, out5, valid_out, ert);
+cudaError_t launch_compact(const DevScene* sc, const SampleSrc& src, long long n, int* list, int* counter, float* out5,
+                           uint8_t* valid_out, cudaStream_t st) {
+  compact_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(sc, src, n, list, counter, out5, valid_out);
   return cudaGetLastError();
 }
 cudaError_t launch_shade_simt(const DevScene* sc, const DevWeightsF32* W, const SampleSrc& src, const int* list,
-                              const int* counter, long long n_max, int query_mode, float* out5, int num_sms,
+                              const int* counter, long long n_max, int query_mode, const ShadeOut& so, int num_sms,
                               cudaStream_t st) {
   static std::atomic<bool> attr_set[64];   // function attributes are per device (setting them twice is harmless)
   int dev = 0;
@@ -693,16 +806,32 @@ cudaError_t launch_shade_simt(const DevScene* sc, const DevWeightsF32* W, const 
     if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   int grid = grid_for(n_max, TS, num_sms);
-  shade_simt_kernel<<<grid, NT, SHADE_SMEM_BYTES, st>>>(sc, W, src, list, counter, query_mode, out5);
+  shade_simt_kernel<<<grid, NT, SHADE_SMEM_BYTES, st>>>(sc, W, src, list, counter, query_mode, so);
   return cudaGetLastError();
 }
-cudaError_t launch_composite(const float* rgba, const float* z, int r0, int nr, int S, int S_eval, long long plane, float* color,
-                             float* depth, float* alpha, float* sdf, float* contrib, cudaStream_t st) {
-  composite_kernel<<<grid_for((long long)nr * 32, 128, 148 * 64), 128, 0, st>>>(rgba, z, r0, nr, S, S_eval, plane, color, depth, alpha, sdf, contrib);
+cudaError_t launch_composite(const int* list, const float2* ao, const float* rgb, const int* start0, const int* cnt0,
+                             const int* start1, const int* cnt1, const float* zbuf, const float* ray_nf, int r0, int nr, int S,
+                             long long plane, float* color, float* depth, float* alpha, float* sdf, float* ray_alpha, float* cw,
+                             cudaStream_t st) {
+  const RaySeg s0{start0, cnt0}, s1{start1, cnt1};
+  composite_kernel<<<grid_for((long long)nr * 32, 128, 148 * 64), 128, 0, st>>>(list, ao, rgb, s0, s1, start1 ? 2 : 1, zbuf, ray_nf, r0, nr,
+                                                                               S, plane, color, depth, alpha, sdf, ray_alpha, cw);
   return cudaGetLastError();
 }
-cudaError_t launch_importance(const float* contrib, const float* z, int nr, int Sc, int Sf, float* zout, cudaStream_t st) {
-  importance_kernel<<<grid_for(nr, 64, 1 << 30), 64, 0, st>>>(contrib, z, nr, Sc, Sf, zout);
+cudaError_t launch_resample(const int* list, const float* cw, const int* start0, const int* cnt0, const int* start1, const int* cnt1,
+                            const float* ray_nf, int nr, int Sc, int Sf, float* zout, float* contrib_out, cudaStream_t st) {
+  const RaySeg s0{start0, cnt0}, s1{start1, cnt1};
+  const size_t smem = (size_t)RES_WARPS * (4 * Sc + 2 * Sf) * sizeof(float);
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire))) {
+    cudaError_t e = cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RES_WARPS * (4 * MAX_SC + 2 * MAX_SF) * sizeof(float)));
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
+  }
+  resample_kernel<<<grid_for(nr, RES_WARPS, 148 * 16), RES_WARPS * 32, smem, st>>>(list, cw, s0, s1, start1 ? 2 : 1, ray_nf, nr, Sc, Sf, zout,
+                                                                               contrib_out);
   return cudaGetLastError();
 }
 int max_coarse_samples() { return MAX_SC; }

@@ -185,6 +185,18 @@ __host__ __device__ constexpr int geo_dcol(int stage) { return stage == 3 ? 192 
 
 constexpr uint32_t H2_ONE = 0x00003C00u;   // fp16 pair (1.0, 0.0): the activation column that multiplies the bias row
 
+#ifdef KPN_STAGE_TIMING
+// Instrumented build only (tools/stage_times.py): cycle stamps of one issuer warp (block 0, slot 0), per tile:
+// [0] tile start, [1] stage-0 input built, then per stage s: [2+5s] own arrive done, [3+5s] every row warp of the pair has
+// arrived, [4+5s] MMAs issued + committed, [5+5s] accumulator complete (this warp woke up), [6+5s] epilogue done.
+constexpr int TIM_TILES = 48, TIM_WORDS = 32;
+__device__ unsigned long long kpn_tim[2 * TIM_TILES * TIM_WORDS];   // rows [0, TIM_TILES): the issuer warp (h = 0); then its h = 1 partner
+__device__ int kpn_tim_tile[2];   // tiles each of the two warps has recorded
+#define TIM(idx) do { if (tim_on && lane == 0) kpn_tim[tim_row * TIM_WORDS + (idx)] = clock64(); } while (0)
+#else
+#define TIM(idx) do { } while (0)
+#endif
+
 struct GeoXch { float g0, rad; uint32_t lat[6]; };   // what the h = 1 thread of a row hands to its h = 0 partner (32 bytes)
 
 struct GeoCtx {
@@ -223,35 +235,43 @@ template <int NK, int STAGE>
 __device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint32_t lo_delta, int lo_mask, uint32_t el);
 // issuer warp only: once every row warp of the pair has signalled this stage's input, issue its MMAs
 template <int NK, int STAGE>
-__device__ __forceinline__ void geo_mma(GeoCtx& c) {
+__device__ __forceinline__ void geo_mma(GeoCtx& c, bool tim_on = false, int tim_row = 0, int lane = 0) {
   if (c.issuer) {
     tc::mbar_wait(c.a_ready, c.pha, 0x10u + (uint32_t)STAGE);
     c.pha ^= 1u;
     tc::fence_after_sync();
+    TIM(3 + 5 * STAGE);
     geo_issue<NK, STAGE>(c.slot_tm, c.wlo0, c.lod, c.lo_mask, c.el);
     tc::mma_commit2_el(c.acc_ready, c.el);
+    TIM(4 + 5 * STAGE);
   }
 }
 __device__ __forceinline__ float gsum(const GeoCtx& c, float x) {
   return x + __shfl_sync(FULL, x, c.l1) + __shfl_sync(FULL, x, c.l2);
 }
 
-// softplus(beta=100) of two accumulators -> packed fp16 pair, on packed halves throughout: x is rounded to fp16 first (the
-// result is an fp16 activation anyway), y = max(x,0) + e*g(e) with e = exp(-100|x|) from ONE ex2 per element and g a cubic
-// (max error of e*g(e) against log1p(e)/100: 7e-7; rms error of the fp16 pipeline = that of rounding the exact softplus).
+// softplus(beta=100) of two accumulators -> packed fp16 pair, on packed halves and WITHOUT the special-function unit: x is
+// rounded to fp16 first (the result is an fp16 activation anyway), y = max(x,0) + c(|x|) with the correction
+// c(t) = log1p(exp(-100 t))/100 ~ q^3 (a0 + a1 q + a2 q^2), q = sat(1 - t/0.08)  (minimax fit, fp16 coefficients): 8 instructions
+// per pair (F2FP, HFMA2.SAT, 2 HMUL2, 3 HFMA2, HMNMX2).  Against the exact softplus over every fp16 input the error is
+// <= 2.8e-5 (rms 9e-6; rounding the exact result to fp16 alone: 1.9e-5 / 2.5e-6), and the rendered RGB error is unchanged
+// (tools/err_budget.py: 7.6e-4 vs 7.7e-4 max on the bench-scene tile).  The previous form took one MUFU.EX2 per ELEMENT; at 4
+// lanes/clk/quarter the three 128-wide epilogues of a tile kept the XU pipe busy for 1.5k cycles per warp and throttled MIO.
 __device__ __forceinline__ uint32_t sp_pair(uint32_t a0, uint32_t a1) {
   const __half2 xh = __floats2half2_rn(u2f(a0), u2f(a1));
-  const uint32_t kt = 0xd882d882u;   // -144.25 = fp16(-100 * log2(e))
-  const uint32_t k3 = 0x90d090d0u, k2 = 0x189f189fu, k1 = 0x9cd39cd3u, k0 = 0x211b211bu;   // -5.875e-4, 2.2564e-3, -4.7112e-3, 9.9716e-3
-  const __half2 t = __hmul2(__habs2(xh), *reinterpret_cast<const __half2*>(&kt));
-  uint32_t eu;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(eu) : "r"(*reinterpret_cast<const uint32_t*>(&t)));
-  const __half2 e = *reinterpret_cast<const __half2*>(&eu);
-  __half2 g = __hfma2(e, *reinterpret_cast<const __half2*>(&k3), *reinterpret_cast<const __half2*>(&k2));
-  g = __hfma2(g, e, *reinterpret_cast<const __half2*>(&k1));
-  g = __hfma2(g, e, *reinterpret_cast<const __half2*>(&k0));
+  const uint32_t k_it = 0xca40ca40u;   // -12.5 = -1 / 0.08
+  const uint32_t k_one = 0x3c003c00u;
+  const uint32_t a2 = 0x24c724c7u, a1c = 0xa459a459u, a0c = 0x1d631d63u;   // 0.018666, -0.016988, 0.00526 (fp16)
+  const uint32_t xa = *reinterpret_cast<const uint32_t*>(&xh) & 0x7fff7fffu;   // |x| (folds into the HFMA2 as an operand modifier)
+  uint32_t q;
+  asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(xa), "r"(k_it), "r"(k_one));
+  const __half2 qh = *reinterpret_cast<const __half2*>(&q);
+  const __half2 q2 = __hmul2(qh, qh);
+  const __half2 q3 = __hmul2(q2, qh);
+  __half2 p = __hfma2(*reinterpret_cast<const __half2*>(&a2), qh, *reinterpret_cast<const __half2*>(&a1c));
+  p = __hfma2(p, qh, *reinterpret_cast<const __half2*>(&a0c));
   const uint32_t zero = 0u;
-  const __half2 y = __hfma2(g, e, __hmax2(xh, *reinterpret_cast<const __half2*>(&zero)));
+  const __half2 y = __hfma2(p, q3, __hmax2(xh, *reinterpret_cast<const __half2*>(&zero)));
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
@@ -361,10 +381,18 @@ template <int NK, bool PREF>
 __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restrict__ wp2, GeoXch* __restrict__ xch,
                                          const SampleSrc& src, const int* __restrict__ list, int count, int tile, int next_tile,
                                          int next2_tile, int& nid, uint32_t* __restrict__ fb, int parity, GeoPre& pre, GeoCtx& cx,
-                                         int q4, int h, int lane, int bar_id, int query_mode, float* __restrict__ out5,
+                                         int q4, int h, int lane, int bar_id, int query_mode, const ShadeOut& so,
                                          uint4* __restrict__ lat_out, int2* __restrict__ list2, int* __restrict__ count2) {
   constexpr int NP = NK / 2, PA = tc_l0_pa(NK), FA = tc_l0_fa(NK);
   const uint32_t A = cx.tm;
+#ifdef KPN_STAGE_TIMING
+  const bool tim_on = blockIdx.x == 0 && bar_id == 1 && kpn_tim_tile[h] < TIM_TILES;   // slot 0, lane quarter 0 of the leader CTA
+  const int tim_row = tim_on ? h * TIM_TILES + kpn_tim_tile[h] : 0;
+#else
+  constexpr bool tim_on = false;
+  constexpr int tim_row = 0;
+#endif
+  TIM(0);
   const int g = lane / 3;
   const int v = lane - 3 * g;           // lanes 30,31 replay views 0,1 of the warp's last sample (results unused)
   const int si = tile * SPT + q4 * SPW + min(g, SPW - 1);
@@ -471,7 +499,9 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     if (h == 1 && w == 4) return;
     taps_stage<2>(pwt, pr, fb, h == 0 ? 4 * w : (w == 3 ? 32 + 4 * (parity ^ 1) : 2 * FG + 4 * w));
   };
+  TIM(1);
   geo_signal(cx, lane);
+  TIM(2);
   // window 0: position of the next tile's sample (its id was fetched during the previous tile; reference src/model.py:1057:
   // p = cam_pos + dir * z, or an explicit query point) and the id of the tile after that
   float nl[7];
@@ -479,7 +509,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   if (pf) {
     if (src.mode == 0) {
       const int r = nid / src.S;
-      nl[0] = __ldg(src.z + nid);
+      nl[0] = src.z ? __ldg(src.z + nid) : coarse_depth(__ldg(src.ray_nf + 2 * r), __ldg(src.ray_nf + 2 * r + 1), nid - r * src.S, src.S);
       nl[1] = __ldg(src.ray_d + 3 * r); nl[2] = __ldg(src.ray_d + 3 * r + 1); nl[3] = __ldg(src.ray_d + 3 * r + 2);
       nl[4] = __ldg(src.o); nl[5] = __ldg(src.o + 1); nl[6] = __ldg(src.o + 2);
     } else {
@@ -489,8 +519,9 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   }
   const uint32_t dh = A + 128u + 64u * (uint32_t)h, ah = A + 32u * (uint32_t)h;
   // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720); thread 0 writes the bias chunk, thread 1 the feat8 | bias chunk
-  geo_mma<NK, 0>(cx);
+  geo_mma<NK, 0>(cx, tim_on, tim_row, lane);
   geo_wait(cx);
+  TIM(5);
   if (pf) {
     pre.id = nid;
     if (src.mode == 0) { pre.p[0] = nl[4] + nl[1] * nl[0]; pre.p[1] = nl[5] + nl[2] * nl[0]; pre.p[2] = nl[6] + nl[3] * nl[0]; }
@@ -504,10 +535,13 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     tc::tmem_st8(A + 64, b);
   }
+  TIM(6);
   geo_signal(cx, lane);
+  TIM(7);
   if (pf) win_issue(0);
-  geo_mma<NK, 1>(cx);
+  geo_mma<NK, 1>(cx, tim_on, tim_row, lane);
   geo_wait(cx);
+  TIM(10);
   if (pf) win_stage(0);
   geo_epi_sp(dh, ah, false);
   if (h == 1) {
@@ -524,18 +558,24 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     }
     tc::tmem_st8(A + 64, b);
   }
+  TIM(11);
   geo_signal(cx, lane);
+  TIM(12);
   if (pf) win_issue(1);
-  geo_mma<NK, 2>(cx);
+  geo_mma<NK, 2>(cx, tim_on, tim_row, lane);
   geo_wait(cx);
+  TIM(15);
   if (pf) win_stage(1);
   geo_epi_sp(dh, ah, h == 1);
+  TIM(16);
   geo_signal(cx, lane);
+  TIM(17);
   if (pf) win_issue(2);
   // ---- view pooling: weighted mean || variance over the 3 lanes of the group (src/utils.py:722-748); this thread owns 32
   //      of the 64 feature columns; the density tail's inputs are kept to two fp16 terms (hi | lo)
-  geo_mma<NK, 3>(cx);
+  geo_mma<NK, 3>(cx, tim_on, tim_row, lane);
   geo_wait(cx);
+  TIM(20);
   if (pf) win_stage(2);
   {
     uint32_t r[32];
@@ -564,11 +604,14 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
       tc::tmem_st8(A + 128, b);
     }
   }
+  TIM(21);
   geo_signal(cx, lane);
+  TIM(22);
   if (pf) win_issue(3);
   // ---- P0 (softplus, two fp16 terms out) | compress (linear; this thread keeps 12 of the 24 latent values as 6 fp16 pairs)
-  geo_mma<NK, 4>(cx);
+  geo_mma<NK, 4>(cx, tim_on, tim_row, lane);
   geo_wait(cx);
+  TIM(25);
   if (pf) win_stage(3);
   uint32_t latp[6];
   {
@@ -605,11 +648,14 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
       tc::tmem_st8(A + 64, b);
     }
   }
+  TIM(26);
   geo_signal(cx, lane);
+  TIM(27);
   if (pf) win_issue(4);
   // ---- P1 (softplus) then the 64->2 density head in fp32 on the CUDA cores: each thread a partial dot over its 32 columns
-  geo_mma<NK, 5>(cx);
+  geo_mma<NK, 5>(cx, tim_on, tim_row, lane);
   geo_wait(cx);
+  TIM(30);
   if (pf) win_stage(4);
   float g0 = 0.0f, rad = 0.0f;
   {
@@ -631,6 +677,10 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     rad = gsum(cx, rad);
   }
   // ---- the h = 1 thread hands its partial sums and latent half to its partner (same row, other warp) through shared memory
+  TIM(31);
+#ifdef KPN_STAGE_TIMING
+  if (tim_on && lane == 0) kpn_tim_tile[h] = tim_row - h * TIM_TILES + 1;
+#endif
   GeoXch* xr = xch + (32 * q4 + lane);
   if (h == 1) {
     *reinterpret_cast<uint4*>(xr) = make_uint4(__float_as_uint(g0), __float_as_uint(rad), latp[0], latp[1]);
@@ -647,11 +697,14 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   //      pass, and the colour work list (a sample with alpha == 0 composites with weight exactly 0: skipping it is exact)
   {
     const bool need = writer && (query_mode != 0 || rad > 0.0f);
+    const int lpos = so.list_base + si;   // this sample's absolute position in the work list
     if (writer) {
-      float* o = out5 + 5ll * id;
-      if (query_mode) { o[0] = g0; o[1] = rad; }
-      else { o[0] = fmaxf(rad, 0.0f); o[1] = g0; }
-      o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
+      if (query_mode) {
+        float* o = so.out5 + 5ll * id;
+        o[0] = g0; o[1] = rad; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
+      } else {
+        so.ao[lpos] = make_float2(fmaxf(rad, 0.0f), g0);   // compact record; the colour (if alpha > 0) follows from the colour kernel
+      }
     }
     const unsigned m = __ballot_sync(FULL, need);
     if (m) {
@@ -661,7 +714,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
       pos = __shfl_sync(FULL, pos, leader);
       if (need) {
         pos += __popc(m & ((1u << lane) - 1u));
-        list2[pos] = make_int2(pos, id);
+        list2[pos] = make_int2(lpos, id);   // x: position in the first work list (where the colour goes), y: sample id
         lat_out[3ll * pos + 0] = make_uint4(latp[0], latp[1], latp[2], latp[3]);
         lat_out[3ll * pos + 1] = make_uint4(latp[4], latp[5], x0.z, x0.w);
         lat_out[3ll * pos + 2] = x1;
@@ -677,13 +730,14 @@ __device__ __forceinline__ void col_mma(RowCtx& c);
 template <int NK>
 __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, const SampleSrc& src,
                                            const int2* __restrict__ list2, int count, int tile, RowCtx& cx, int roww, int lane,
-                                           const uint4* __restrict__ lat_in, float* __restrict__ out5) {
+                                           const uint4* __restrict__ lat_in, int query_mode, const ShadeOut& so) {
   const uint32_t R0 = cx.R0, R1 = cx.R1;
   const int g = lane / 3;
   const int v = lane - 3 * g;
   const int si = tile * SPT + roww * SPW + min(g, SPW - 1);
   const bool writer = (lane < 3 * SPW) && (v == 0) && (si < count);
-  const int2 ent = list2[min(si, count - 1)];
+  const int lslot = min(si, count - 1);   // entry index == slot of its latent in the scratch buffer
+  const int2 ent = list2[lslot];
   const int id = ent.y;
   float p[3], d[3];
   fetch_sample(src, id, p, d);
@@ -691,7 +745,7 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
   float lat[24];
   {
     uint4 w[3];
-    w[0] = __ldg(lat_in + 3ll * ent.x + 0); w[1] = __ldg(lat_in + 3ll * ent.x + 1); w[2] = __ldg(lat_in + 3ll * ent.x + 2);
+    w[0] = __ldg(lat_in + 3ll * lslot + 0); w[1] = __ldg(lat_in + 3ll * lslot + 1); w[2] = __ldg(lat_in + 3ll * lslot + 2);
     const __half2* hp = reinterpret_cast<const __half2*>(w);
 #pragma unroll
     for (int i = 0; i < 12; ++i) { float2 t2 = __half22float2(hp[i]); lat[2 * i] = t2.x; lat[2 * i + 1] = t2.y; }
@@ -865,8 +919,8 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
     float inv = 1.0f / gsum(cx, e);
     float r0 = gsum(cx, e * rgb[0]) * inv, r1 = gsum(cx, e * rgb[1]) * inv, r2 = gsum(cx, e * rgb[2]) * inv;
     if (writer) {
-      float* o = out5 + 5ll * id;
-      o[2] = r0; o[3] = r1; o[4] = r2;
+      float* o = query_mode ? so.out5 + 5ll * id + 2 : so.rgb + 3ll * ent.x;
+      o[0] = r0; o[1] = r1; o[2] = r2;
     }
   }
 }
@@ -976,7 +1030,7 @@ template <int NK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEO_THREADS, 1)
 shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
                  int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
-                 int query_mode, float* __restrict__ out5, uint4* __restrict__ lat_out, int2* __restrict__ list2,
+                 int query_mode, ShadeOut so, uint4* __restrict__ lat_out, int2* __restrict__ list2,
                  int* __restrict__ count2, int relaxed_arrive) {
   extern __shared__ __align__(1024) uint8_t wsm[];
   // barriers: [0] weights | per slot s: [1+2s] a_ready (one arrival per row warp of the pair = 16; only the leader's copy is
@@ -1047,7 +1101,7 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
       // a tile index past the end is a ghost tile: it replays the last sample, takes part in every barrier, writes nothing
       const int Pn = P + ncl * NSLOT, Pn2 = Pn + ncl * NSLOT;
       geo_tile<NK, PREF>(scs, wp2, xch[slot], src, list, count, 2 * P + (int)rank, 2 * Pn < ntiles ? 2 * Pn + (int)rank : -1,
-                         2 * Pn2 < ntiles ? 2 * Pn2 + (int)rank : -1, nid, fb, parity, pre, cx, q4, h, lane, bar_id, query_mode, out5,
+                         2 * Pn2 < ntiles ? 2 * Pn2 + (int)rank : -1, nid, fb, parity, pre, cx, q4, h, lane, bar_id, query_mode, so,
                          lat_out, list2, count2);
       parity ^= 1;
     }
@@ -1065,7 +1119,7 @@ template <int NK>
 __global__ void __launch_bounds__(TCC_THREADS, 1)
 shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
                    SampleSrc src, const int2* __restrict__ list2, const int* __restrict__ count_ptr,
-                   const uint4* __restrict__ lat_in, float* __restrict__ out5) {
+                   const uint4* __restrict__ lat_in, int query_mode, ShadeOut so) {
   extern __shared__ __align__(1024) uint8_t wsm[];
   __shared__ uint64_t bars[1 + 2 * CSLOT];   // [0] weights | per slot: a_ready, acc_ready
   __shared__ uint32_t tmem_base_s;
@@ -1105,7 +1159,7 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
     cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
     cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
     for (int tile = blockIdx.x * CSLOT + slot; tile < ntiles; tile += gridDim.x * CSLOT)
-      color_tile<NK>(scs, C, src, list2, count, tile, cx, roww, lane, lat_in, out5);
+      color_tile<NK>(scs, C, src, list2, count, tile, cx, roww, lane, lat_in, query_mode, so);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -1120,8 +1174,8 @@ bool tc_supported(int n_views, int n_kpt, int sp_level) { return n_views == 3 &&
 
 template <int NK>
 static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term,
-                                  const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
-                                  uint4* lat, int2* list2, int* count2, int num_sms, cudaEvent_t after_geo, cudaStream_t st) {
+                                  const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode,
+                                  const ShadeOut& so, uint4* lat, int2* list2, int* count2, int num_sms, cudaEvent_t after_geo, cudaStream_t st) {
   constexpr TcPlan plan = make_tc_plan(NK);
   const size_t smem_geo = plan.st[GEO_NSTAGE].off + (geo_pref(NK) ? (size_t)NSLOT * GEO_FW * 128 * 4 : 0);
   const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
@@ -1143,24 +1197,25 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   // which stages get the W_lo pass (bits 0..5) and the A_lo pass (bits 6, 7 for stages 4, 5); KPN_LO_MASK overrides (experiments)
   static const int lo_env = [] { const char* e = getenv("KPN_LO_MASK"); return e ? (int)strtol(e, nullptr, 0) : -1; }();
   two_term = two_term ? (lo_env >= 0 ? lo_env : 0xFF) : 0xC0;
-  shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, out5, lat, list2,
+  shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat, list2,
                                                            count2, relaxed_arrive);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (after_geo) { e = cudaEventRecord(after_geo, st); if (e != cudaSuccess) return e; }
   long long g = (max_tiles + CSLOT - 1) / CSLOT;
   grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
-  shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, count2, lat, out5);
+  shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, count2, lat, query_mode, so);
   return cudaGetLastError();
 }
 
 cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term, int n_kpt,
-                            const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode, float* out5,
-                            void* lat_scratch, void* list2, int* count2, int num_sms, cudaEvent_t after_geo, cudaStream_t st) {
+                            const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode,
+                            const ShadeOut& so, void* lat_scratch, void* list2, int* count2, int num_sms, cudaEvent_t after_geo,
+                            cudaStream_t st) {
   if (n_kpt == 18)
-    return launch_tc_impl<18>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
+    return launch_tc_impl<18>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, so, (uint4*)lat_scratch,
                               (int2*)list2, count2, num_sms, after_geo, st);
-  return launch_tc_impl<24>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, out5, (uint4*)lat_scratch,
+  return launch_tc_impl<24>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, so, (uint4*)lat_scratch,
                             (int2*)list2, count2, num_sms, after_geo, st);
 }
 
@@ -1182,6 +1237,26 @@ cudaError_t tc_watchdog_clear_async(cudaStream_t st) {
   cudaError_t e = cudaGetSymbolAddress(&p, tc::kpn_wd);
   if (e != cudaSuccess) return e;
   return cudaMemsetAsync(p, 0, 8 * sizeof(unsigned int), st);
+}
+
+// stage-timing dump of the instrumented build (KPN_STAGE_TIMING); returns cudaErrorNotSupported otherwise
+cudaError_t tc_stage_times(unsigned long long* out, int n_words, int* n_tiles) {
+#ifdef KPN_STAGE_TIMING
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return e;
+  int nt[2] = {0, 0};
+  e = cudaMemcpyFromSymbol(nt, kpn_tim_tile, sizeof(nt));
+  if (e != cudaSuccess) return e;
+  *n_tiles = nt[0] < nt[1] ? nt[0] : nt[1];
+  const size_t bytes = sizeof(unsigned long long) * (size_t)(n_words < 2 * TIM_TILES * TIM_WORDS ? n_words : 2 * TIM_TILES * TIM_WORDS);
+  e = cudaMemcpyFromSymbol(out, kpn_tim, bytes);
+  if (e != cudaSuccess) return e;
+  const int zero[2] = {0, 0};
+  return cudaMemcpyToSymbol(kpn_tim_tile, zero, sizeof(zero));
+#else
+  (void)out; (void)n_words; (void)n_tiles;
+  return cudaErrorNotSupported;
+#endif
 }
 
 size_t tc_pair_blob_bytes(int n_kpt) { return 2 * (size_t)make_tc_plan(n_kpt).st[GEO_NSTAGE].off; }

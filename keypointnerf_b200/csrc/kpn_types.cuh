@@ -68,13 +68,25 @@ struct DevWeightsF32 {
 
 // Where the samples of a shading launch come from.
 struct SampleSrc {
-  int mode;            // 0: rays (p = o + d*z[ray*S+i]),  1: explicit points
+  int mode;            // 0: rays (p = o + d*z(ray, i)),  1: explicit points
   int S;               // samples per ray (mode 0)
   const float* ray_d;  // (R,3) unit directions
-  const float* z;      // (R,S) depths
+  const float* z;      // (R,S) depths; nullptr: the coarse pass' uniform depths, recomputed from ray_nf (never stored)
+  const float* ray_nf; // (R,2) near/far along the ray (used when z == nullptr)
   const float* pts;    // (n,3)   (mode 1)
   const float* view;   // (n,3)   (mode 1)
   const float* o;      // (3) ray origin on device (mode 0)
+};
+
+// Where a shading launch puts its per-sample results.
+//   query mode (KeypointNeRF.query): out5[id] = [sdf_raw, rad, r, g, b], dense by sample id.
+//   render mode: compact records indexed by the sample's position in the work list (list_base + index): ao[pos] = (alpha, sdf),
+//   rgb[pos] = blended colour (written only for samples with alpha > 0).  Nothing is stored for invalid samples.
+struct ShadeOut {
+  float* out5;     // query mode, else nullptr
+  float2* ao;      // render mode
+  float* rgb;      // render mode, 3 floats per list position
+  int list_base;   // absolute list position of this launch's first entry
 };
 
 // Segment of a ray's samples handled by one compaction pass of an early-ray-termination render (s_hi == 0: all samples).
