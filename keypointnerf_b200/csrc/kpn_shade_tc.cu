@@ -382,7 +382,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
                                          const SampleSrc& src, const int* __restrict__ list, int count, int tile, int next_tile,
                                          int next2_tile, int& nid, uint32_t* __restrict__ fb, int parity, GeoPre& pre, GeoCtx& cx,
                                          int q4, int h, int lane, int bar_id, int query_mode, const ShadeOut& so,
-                                         uint4* __restrict__ lat_out, int2* __restrict__ list2, int* __restrict__ count2) {
+                                         uint4* __restrict__ lat_out) {
   constexpr int NP = NK / 2, PA = tc_l0_pa(NK), FA = tc_l0_fa(NK);
   const uint32_t A = cx.tm;
 #ifdef KPN_STAGE_TIMING
@@ -693,33 +693,65 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   const uint4 x0 = *reinterpret_cast<const uint4*>(xr), x1 = *(reinterpret_cast<const uint4*>(xr) + 1);
   g0 += __uint_as_float(x0.x) + wp2[128];
   rad += __uint_as_float(x0.y) + wp2[129];
-  // ---- outputs of the geometry pass: alpha / sdf (eval_func, src/model.py:978-997), the compressed latent for the colour
-  //      pass, and the colour work list (a sample with alpha == 0 composites with weight exactly 0: skipping it is exact)
+  // ---- outputs of the geometry pass: alpha / sdf (eval_func, src/model.py:978-997) and, where a colour will be needed
+  //      (density > 0: a sample with alpha == 0 composites with weight exactly 0, skipping its colour is exact; every valid
+  //      sample in query mode), the compressed latent at the sample's own list index.  The colour work list is built from the
+  //      alpha records by colour_list_kernel afterwards: no atomic round trip sits in this kernel's tile loop.
   {
     const bool need = writer && (query_mode != 0 || rad > 0.0f);
-    const int lpos = so.list_base + si;   // this sample's absolute position in the work list
     if (writer) {
       if (query_mode) {
         float* o = so.out5 + 5ll * id;
         o[0] = g0; o[1] = rad; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
       } else {
-        so.ao[lpos] = make_float2(fmaxf(rad, 0.0f), g0);   // compact record; the colour (if alpha > 0) follows from the colour kernel
+        so.ao[so.list_base + si] = make_float2(fmaxf(rad, 0.0f), g0);   // compact record at the sample's absolute list position
       }
     }
-    const unsigned m = __ballot_sync(FULL, need);
-    if (m) {
-      const int leader = __ffs(m) - 1;
-      int pos = 0;
-      if (lane == leader) pos = atomicAdd(count2, __popc(m));
-      pos = __shfl_sync(FULL, pos, leader);
-      if (need) {
-        pos += __popc(m & ((1u << lane) - 1u));
-        list2[pos] = make_int2(lpos, id);   // x: position in the first work list (where the colour goes), y: sample id
-        lat_out[3ll * pos + 0] = make_uint4(latp[0], latp[1], latp[2], latp[3]);
-        lat_out[3ll * pos + 1] = make_uint4(latp[4], latp[5], x0.z, x0.w);
-        lat_out[3ll * pos + 2] = x1;
-      }
+    if (need) {
+      lat_out[3ll * si + 0] = make_uint4(latp[0], latp[1], latp[2], latp[3]);
+      lat_out[3ll * si + 1] = make_uint4(latp[4], latp[5], x0.z, x0.w);
+      lat_out[3ll * si + 2] = x1;
     }
+  }
+}
+
+// Colour work list: the entries of the first list whose sample needs a colour (alpha > 0), in list order, as (index into the
+// first list, sample id).  Block-aggregated append (one atomic per 1024 entries).
+__global__ void __launch_bounds__(256)
+colour_list_kernel(const int* __restrict__ list, const int* __restrict__ count_ptr, const float2* __restrict__ ao, int list_base,
+                   int2* __restrict__ list2, int* __restrict__ count2) {
+  __shared__ int s_cnt[8];
+  __shared__ int s_base;
+  const int count = *count_ptr;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = blockIdx.x * 1024; base < count; base += gridDim.x * 1024) {   // block-uniform trip count
+    bool ok[4];
+    unsigned m[4];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * 256 + threadIdx.x;
+      ok[j] = i < count && ao[list_base + i].x > 0.0f;
+      m[j] = __ballot_sync(FULL, ok[j]);
+      mine += __popc(m[j]);
+    }
+    if (lane == 0) s_cnt[wid] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(count2, tot) : 0;
+    }
+    __syncthreads();
+    int pos = s_base + s_cnt[wid];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * 256 + threadIdx.x;
+      if (ok[j]) list2[pos + __popc(m[j] & ((1u << lane) - 1u))] = make_int2(i, list[i]);
+      pos += __popc(m[j]);
+    }
+    __syncthreads();
   }
 }
 
@@ -729,15 +761,18 @@ __device__ __forceinline__ void col_mma(RowCtx& c);
 
 template <int NK>
 __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, const SampleSrc& src,
-                                           const int2* __restrict__ list2, int count, int tile, RowCtx& cx, int roww, int lane,
+                                           const int2* __restrict__ list2, const int* __restrict__ list1, int count, int tile,
+                                           RowCtx& cx, int roww, int lane,
                                            const uint4* __restrict__ lat_in, int query_mode, const ShadeOut& so) {
   const uint32_t R0 = cx.R0, R1 = cx.R1;
   const int g = lane / 3;
   const int v = lane - 3 * g;
   const int si = tile * SPT + roww * SPW + min(g, SPW - 1);
   const bool writer = (lane < 3 * SPW) && (v == 0) && (si < count);
-  const int lslot = min(si, count - 1);   // entry index == slot of its latent in the scratch buffer
-  const int2 ent = list2[lslot];
+  // entry: x = index into the first work list (where the latent sits and, + list_base, where the colour goes), y = sample id;
+  // query mode shades every valid sample: the first list itself is the work list
+  const int e = min(si, count - 1);
+  const int2 ent = list2 ? list2[e] : make_int2(e, list1[e]);
   const int id = ent.y;
   float p[3], d[3];
   fetch_sample(src, id, p, d);
@@ -745,7 +780,7 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
   float lat[24];
   {
     uint4 w[3];
-    w[0] = __ldg(lat_in + 3ll * lslot + 0); w[1] = __ldg(lat_in + 3ll * lslot + 1); w[2] = __ldg(lat_in + 3ll * lslot + 2);
+    w[0] = __ldg(lat_in + 3ll * ent.x + 0); w[1] = __ldg(lat_in + 3ll * ent.x + 1); w[2] = __ldg(lat_in + 3ll * ent.x + 2);
     const __half2* hp = reinterpret_cast<const __half2*>(w);
 #pragma unroll
     for (int i = 0; i < 12; ++i) { float2 t2 = __half22float2(hp[i]); lat[2 * i] = t2.x; lat[2 * i + 1] = t2.y; }
@@ -919,7 +954,7 @@ __device__ __forceinline__ void color_tile(const SceneS& sc, const TcConsts& C, 
     float inv = 1.0f / gsum(cx, e);
     float r0 = gsum(cx, e * rgb[0]) * inv, r1 = gsum(cx, e * rgb[1]) * inv, r2 = gsum(cx, e * rgb[2]) * inv;
     if (writer) {
-      float* o = query_mode ? so.out5 + 5ll * id + 2 : so.rgb + 3ll * ent.x;
+      float* o = query_mode ? so.out5 + 5ll * id + 2 : so.rgb + 3ll * (so.list_base + ent.x);
       o[0] = r0; o[1] = r1; o[2] = r2;
     }
   }
@@ -1030,8 +1065,7 @@ template <int NK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEO_THREADS, 1)
 shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
                  int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
-                 int query_mode, ShadeOut so, uint4* __restrict__ lat_out, int2* __restrict__ list2,
-                 int* __restrict__ count2, int relaxed_arrive) {
+                 int query_mode, ShadeOut so, uint4* __restrict__ lat_out, int relaxed_arrive) {
   extern __shared__ __align__(1024) uint8_t wsm[];
   // barriers: [0] weights | per slot s: [1+2s] a_ready (one arrival per row warp of the pair = 16; only the leader's copy is
   //           used), [2+2s] acc_ready (one multicast commit per stage, each CTA waits on its own copy)
@@ -1102,7 +1136,7 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
       const int Pn = P + ncl * NSLOT, Pn2 = Pn + ncl * NSLOT;
       geo_tile<NK, PREF>(scs, wp2, xch[slot], src, list, count, 2 * P + (int)rank, 2 * Pn < ntiles ? 2 * Pn + (int)rank : -1,
                          2 * Pn2 < ntiles ? 2 * Pn2 + (int)rank : -1, nid, fb, parity, pre, cx, q4, h, lane, bar_id, query_mode, so,
-                         lat_out, list2, count2);
+                         lat_out);
       parity ^= 1;
     }
   }
@@ -1118,8 +1152,8 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
 template <int NK>
 __global__ void __launch_bounds__(TCC_THREADS, 1)
 shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wblob,
-                   SampleSrc src, const int2* __restrict__ list2, const int* __restrict__ count_ptr,
-                   const uint4* __restrict__ lat_in, int query_mode, ShadeOut so) {
+                   SampleSrc src, const int2* __restrict__ list2, const int* __restrict__ list1,
+                   const int* __restrict__ count_ptr, const uint4* __restrict__ lat_in, int query_mode, ShadeOut so) {
   extern __shared__ __align__(1024) uint8_t wsm[];
   __shared__ uint64_t bars[1 + 2 * CSLOT];   // [0] weights | per slot: a_ready, acc_ready
   __shared__ uint32_t tmem_base_s;
@@ -1159,7 +1193,7 @@ shade_color_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcC
     cx.l1 = (cx.gb + (lane - cx.gb + 1) % 3) & 31;
     cx.l2 = (cx.gb + (lane - cx.gb + 2) % 3) & 31;
     for (int tile = blockIdx.x * CSLOT + slot; tile < ntiles; tile += gridDim.x * CSLOT)
-      color_tile<NK>(scs, C, src, list2, count, tile, cx, roww, lane, lat_in, query_mode, so);
+      color_tile<NK>(scs, C, src, list2, list1, count, tile, cx, roww, lane, lat_in, query_mode, so);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -1197,14 +1231,24 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   // which stages get the W_lo pass (bits 0..5) and the A_lo pass (bits 6, 7 for stages 4, 5); KPN_LO_MASK overrides (experiments)
   static const int lo_env = [] { const char* e = getenv("KPN_LO_MASK"); return e ? (int)strtol(e, nullptr, 0) : -1; }();
   two_term = two_term ? (lo_env >= 0 ? lo_env : 0xFF) : 0xC0;
-  shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat, list2,
-                                                           count2, relaxed_arrive);
+  shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat,
+                                                           relaxed_arrive);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (after_geo) { e = cudaEventRecord(after_geo, st); if (e != cudaSuccess) return e; }
   long long g = (max_tiles + CSLOT - 1) / CSLOT;
   grid = (int)(g < 1 ? 1 : (g > num_sms ? num_sms : g));
-  shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, count2, lat, query_mode, so);
+  if (query_mode) {   // every valid sample gets a colour: the first list is the colour work list
+    shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, nullptr, list, counter, lat, query_mode, so);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(count2, counter, sizeof(int), cudaMemcpyDeviceToDevice, st);   // statistics: every valid sample was coloured
+  }
+  const long long lb = (n_max + 1023) / 1024;
+  colour_list_kernel<<<(int)(lb < 1 ? 1 : (lb > 148 * 8 ? 148 * 8 : lb)), 256, 0, st>>>(list, counter, so.ao, so.list_base, list2, count2);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  shade_color_kernel<NK><<<grid, TCC_THREADS, smem_col, st>>>(sc, C, wblob, src, list2, nullptr, count2, lat, query_mode, so);
   return cudaGetLastError();
 }
 
