@@ -96,9 +96,9 @@ __device__ __forceinline__ float sample_fg(const DevScene& sc, int v, const Proj
 // (reference src/model.py:729-739).  Also returns the per-view projections.
 __device__ __forceinline__ bool sample_valid(const DevScene& sc, const float p[3], Proj q[MAXV]) {
   bool ok = true;
-  for (int v = 0; v < sc.V; ++v) {
+  for (int v = 0; v < sc.V && ok; ++v) {   // the first view that rejects the sample ends the test (q of the later views is unset)
     q[v] = project_view(sc, v, p);
-    ok = ok && in_frustum(q[v]);
+    ok = in_frustum(q[v]);
   }
   if (ok && sc.use_fg) {
     for (int v = 0; v < sc.V; ++v) ok = ok && (sample_fg(sc, v, q[v]) > 0.1f);

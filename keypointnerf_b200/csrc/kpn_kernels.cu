@@ -147,7 +147,7 @@ __device__ __forceinline__ void ray_for_pixel(const DevScene& sc, const DevTarge
 constexpr int FRONT_WARPS = 8;
 constexpr int FRONT_MAXW = 40;   // ballot words per ray: up to 1280 samples (256 coarse + 1024 fine)
 
-__global__ void __launch_bounds__(FRONT_WARPS * 32)
+__global__ void __launch_bounds__(FRONT_WARPS * 32, 6)
 front_kernel(const DevScene* __restrict__ scp, const DevTarget* __restrict__ tgp, int r0, int nr, int S,
              const float* __restrict__ zbuf, float* __restrict__ ray_d, float* __restrict__ ray_nf,
              int* __restrict__ list, int list_base, int* __restrict__ counter, int* __restrict__ ray_start,
@@ -785,7 +785,17 @@ cudaError_t launch_prep_target(const RawTarget* raw, DevTarget* tg, cudaStream_t
 cudaError_t launch_front(const DevScene* sc, const DevTarget* tg, int r0, int nr, int S, const float* zbuf, float* ray_d,
                          float* ray_nf, int* list, int list_base, int* counter, int* ray_start, int* ray_cnt, const ErtSegment& ert,
                          cudaStream_t st) {
-  front_kernel<<<grid_for(nr, FRONT_WARPS, 148 * 8), FRONT_WARPS * 32, 0, st>>>(sc, tg, r0, nr, S, zbuf, ray_d, ray_nf, list, list_base,
+  // persistent grid: as many blocks as are resident at once (no partial second wave)
+  static std::atomic<int> per_sm{0};
+  int bps = per_sm.load(std::memory_order_acquire);
+  if (bps == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, front_kernel, FRONT_WARPS * 32, 0) != cudaSuccess || bps < 1) bps = 4;
+    per_sm.store(bps, std::memory_order_release);
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  front_kernel<<<grid_for(nr, FRONT_WARPS, sms * bps), FRONT_WARPS * 32, 0, st>>>(sc, tg, r0, nr, S, zbuf, ray_d, ray_nf, list, list_base,
                                                                             counter, ray_start, ray_cnt, ert);
   return cudaGetLastError();
 }

@@ -197,7 +197,7 @@ __device__ int kpn_tim_tile[2];   // tiles each of the two warps has recorded
 #define TIM(idx) do { } while (0)
 #endif
 
-struct GeoXch { float g0, rad; uint32_t lat[6]; };   // what the h = 1 thread of a row hands to its h = 0 partner (32 bytes)
+// (what the h = 1 thread of a row hands to its h = 0 partner at the end of a tile: g0, rad partial sums + 6 latent words)
 
 struct GeoCtx {
   uint32_t tm;          // TMEM address of the slot with this warp's lane quarter
@@ -305,12 +305,12 @@ __device__ __forceinline__ void geo_epi_sp(uint32_t d, uint32_t a, bool bias_tai
 
 // Gather staging (PREF): while a tile's layer-0 MMAs run, each row thread gathers the source-view features of its row of the
 // slot's NEXT tile (the long-latency part of the stage-0 input) into shared memory as packed fp16 pairs; the next tile's build
-// only copies them into tensor memory.  Words per row: 32 feat64 (thread 0 owns [0, FA/2), thread 1 the rest) + 2 x 4 feat8
-// (double-buffered by tile parity: it is consumed two stages after the next prefetch started).  Word w of row r sits at
-// [w * 128 + r] so that a warp's accesses are conflict free.
-constexpr int GEO_FW = 40;
-// shared memory holds the staging buffer next to the weights only for 18 keypoints (24: the layer-0 tile is 12 KB larger)
-__host__ __device__ constexpr bool geo_pref(int n_kpt) { return n_kpt == 18; }
+// only copies them into tensor memory.  Words per row: 32 feat64 (thread 0 owns [0, FA/2), thread 1 the rest) + 4 feat8 (a
+// tile consumes its feat8 words after stage 1, the next tile's are staged after stage 4: one buffer is enough).  Word w of row
+// r sits at [w * 128 + r] so that a warp's accesses are conflict free.  2 slots x 36 words x 128 rows = 36 KB, which fits
+// behind the resident weights for both keypoint counts (18: 173 KB, 24: 185 KB per CTA).
+constexpr int GEO_FW = 36;
+__host__ __device__ constexpr bool geo_pref(int n_kpt) { return n_kpt == 18 || n_kpt == 24; }
 struct GeoPre { int id; float p[3]; };   // the sample this row shades in the slot's next tile
 
 // Asynchronous halves of a bilinear gather: issue the 4 tap loads of float4 groups [g0, g0 + NG) of a channel-last map now,
@@ -370,7 +370,7 @@ __device__ __forceinline__ void geo_prefetch(const SceneS& sc, const SampleSrc& 
     float g8[8];
     gather_f32<2>(sc.f8, v, t8, 0, g8);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) fb[(32 + 4 * parity + i) * 128] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) fb[(32 + i) * 128] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
   }
 }
 
@@ -378,7 +378,7 @@ __device__ __forceinline__ void geo_prefetch(const SceneS& sc, const SampleSrc& 
 // tile's on exit, `nid` the sample id of the next tile on entry and of the tile after that (`next2_tile`) on exit;
 // `next_tile` < 0: nothing to prefetch.
 template <int NK, bool PREF>
-__device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restrict__ wp2, GeoXch* __restrict__ xch,
+__device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restrict__ wp2,
                                          const SampleSrc& src, const int* __restrict__ list, int count, int tile, int next_tile,
                                          int next2_tile, int& nid, uint32_t* __restrict__ fb, int parity, GeoPre& pre, GeoCtx& cx,
                                          int q4, int h, int lane, int bar_id, int query_mode, const ShadeOut& so,
@@ -497,7 +497,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
   };
   auto win_stage = [&](int w) {
     if (h == 1 && w == 4) return;
-    taps_stage<2>(pwt, pr, fb, h == 0 ? 4 * w : (w == 3 ? 32 + 4 * (parity ^ 1) : 2 * FG + 4 * w));
+    taps_stage<2>(pwt, pr, fb, h == 0 ? 4 * w : (w == 3 ? 32 : 2 * FG + 4 * w));
   };
   TIM(1);
   geo_signal(cx, lane);
@@ -548,7 +548,7 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     uint32_t b[8] = {0u, 0u, 0u, 0u, H2_ONE, 0u, 0u, 0u};
     if (PREF) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = fb[(32 + 4 * parity + i) * 128];
+      for (int i = 0; i < 4; ++i) b[i] = fb[(32 + i) * 128];
     } else {
       const Taps t8 = make_taps(q.u, q.v, sc.f8.W, sc.f8.H);
       float g8[8];
@@ -676,21 +676,27 @@ __device__ __forceinline__ void geo_tile(const SceneS& sc, const float* __restri
     g0 = gsum(cx, g0);
     rad = gsum(cx, rad);
   }
-  // ---- the h = 1 thread hands its partial sums and latent half to its partner (same row, other warp) through shared memory
+  // ---- the h = 1 thread hands its partial sums and latent half to its partner (same row = same tensor-memory lane, other warp)
+  //      through 8 tensor-memory columns of that lane: the activation region is dead once the P1 accumulator has arrived, and
+  //      columns [0, 8) belong to the partner's own stage-0 run, which it only rebuilds after it has read them
   TIM(31);
 #ifdef KPN_STAGE_TIMING
   if (tim_on && lane == 0) kpn_tim_tile[h] = tim_row - h * TIM_TILES + 1;
 #endif
-  GeoXch* xr = xch + (32 * q4 + lane);
   if (h == 1) {
-    *reinterpret_cast<uint4*>(xr) = make_uint4(__float_as_uint(g0), __float_as_uint(rad), latp[0], latp[1]);
-    *(reinterpret_cast<uint4*>(xr) + 1) = make_uint4(latp[2], latp[3], latp[4], latp[5]);
-    __threadfence_block();
+    const uint32_t xw[8] = {__float_as_uint(g0), __float_as_uint(rad), latp[0], latp[1], latp[2], latp[3], latp[4], latp[5]};
+    tc::tmem_st8(A, xw);
+    tc::wait_st();
+    tc::fence_before_sync();
     tc::named_arrive(bar_id, 64);
     return;
   }
   tc::named_sync(bar_id, 64);
-  const uint4 x0 = *reinterpret_cast<const uint4*>(xr), x1 = *(reinterpret_cast<const uint4*>(xr) + 1);
+  tc::fence_after_sync();
+  uint32_t xr[8];
+  tc::tmem_ld8(A, xr);
+  tc::wait_ld();
+  const uint4 x0 = make_uint4(xr[0], xr[1], xr[2], xr[3]), x1 = make_uint4(xr[4], xr[5], xr[6], xr[7]);
   g0 += __uint_as_float(x0.x) + wp2[128];
   rad += __uint_as_float(x0.y) + wp2[129];
   // ---- outputs of the geometry pass: alpha / sdf (eval_func, src/model.py:978-997) and, where a colour will be needed
@@ -1073,7 +1079,6 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
   __shared__ uint32_t tmem_base_s;
   __shared__ SceneS scs;
   __shared__ __align__(16) float wp2[132];                 // density head: w[0][64] | w[1][64] | b[2]
-  __shared__ __align__(16) GeoXch xch[NSLOT][128];
   constexpr TcPlan plan = make_tc_plan(NK);
   constexpr uint32_t WBYTES = plan.st[GEO_NSTAGE].off;   // per CTA: half of W_hi + half of W_lo of stages 0..5
   constexpr bool PREF = geo_pref(NK);                    // gather staging buffer behind the weights
@@ -1134,7 +1139,7 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
     for (; 2 * P < ntiles; P += ncl * NSLOT) {
       // a tile index past the end is a ghost tile: it replays the last sample, takes part in every barrier, writes nothing
       const int Pn = P + ncl * NSLOT, Pn2 = Pn + ncl * NSLOT;
-      geo_tile<NK, PREF>(scs, wp2, xch[slot], src, list, count, 2 * P + (int)rank, 2 * Pn < ntiles ? 2 * Pn + (int)rank : -1,
+      geo_tile<NK, PREF>(scs, wp2, src, list, count, 2 * P + (int)rank, 2 * Pn < ntiles ? 2 * Pn + (int)rank : -1,
                          2 * Pn2 < ntiles ? 2 * Pn2 + (int)rank : -1, nid, fb, parity, pre, cx, q4, h, lane, bar_id, query_mode, so,
                          lat_out);
       parity ^= 1;

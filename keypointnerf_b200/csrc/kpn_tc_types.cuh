@@ -30,8 +30,10 @@ struct TcPlan {
 __host__ __device__ constexpr int tc_k0p(int n_kpt) { return ((7 * n_kpt + 64 + 1) + 15) / 16 * 16; }
 // split of the layer-0 input between the two threads of a row: thread 0 builds keypoint pairs [0, PA) and feature
 // channels [0, FA), thread 1 the remaining pairs, the remaining channels and the bias column
-__host__ __device__ constexpr int tc_l0_pa(int n_kpt) { return n_kpt == 18 ? 4 : 6; }
-__host__ __device__ constexpr int tc_l0_fa(int n_kpt) { return n_kpt == 18 ? 40 : 44; }
+// (18 keypoints: 4 | 5 pairs; 24: 4 | 8 pairs -- the second thread starts a tile earlier, its partner writes the tile's outputs;
+// the 40 | 24 channel split keeps one gather plan for both keypoint counts: 10 | 6 float4 groups of feat64)
+__host__ __device__ constexpr int tc_l0_pa(int n_kpt) { return 4 + 0 * n_kpt; }
+__host__ __device__ constexpr int tc_l0_fa(int n_kpt) { return 40 + 0 * n_kpt; }
 
 // K index (fp16 element of the activation row) that input `i` of geometry stage `stage` is multiplied with.
 // Stage 0 inputs: i < 7*n_kpt is encoding element r*n_kpt + k (reference src/spatial.py layout), else feat64 channel.

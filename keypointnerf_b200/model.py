@@ -333,6 +333,45 @@ class KeypointNeRF(nn.Module):
             out["tar_img"] = tar_img.cpu()
         return out
 
+    # ---- camera sweep (reference KeypointNeRFLightningModule.render_novel_views, src/model.py:475-507) ------------
+    @staticmethod
+    def render_views(net, img_in, cam_in, cams_tar, sp_data={}, rank=0, world=1, **config):
+        """Render one source-image set from many target cameras (the 90-camera sweep of ``render_dynamic.py``;
+        SURVEY.md section 8f.2).  Same ``**config`` keys and per-frame result dicts (detached CPU tensors) as
+        ``render_pifu_nerf``, but the encoders run once, the scene is bound once, every frame is enqueued without a host
+        synchronisation and its device-to-host copy runs on a side stream into pinned memory while the next frame renders;
+        the call synchronises once at the end.  ``rank``/``world``: this process renders cameras ``rank::world`` (one process
+        per GPU; the caller gathers the frames it wants, e.g. with ``distributed.gather_views``)."""
+        config = dict(config)
+        feat_geo = config.pop("feat_geo", None)
+        feat_tex = config.pop("feat_tex", None)
+        if feat_geo is None:
+            feat_geo = net.attach_geo_feat(img_in, return_val=True)
+        if feat_tex is None:
+            feat_tex = net.attach_tex_feat(img_in, return_val=True)
+        dev = torch.device("cuda", net._device_index())
+        main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+        frames, inflight = [], []
+        for cam_tar in list(cams_tar)[rank::world]:
+            out = KeypointNeRF._render(net, img_in, cam_in, cam_tar, 1, 0, 0, None, feat_geo, feat_tex, sp_data,
+                                       out_device="cuda", **config)
+            done = torch.cuda.Event()
+            done.record(main)
+            host = {}
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                for k, v in out.items():
+                    h = torch.empty(v.shape[1:] if v.dim() == 4 else v.shape, dtype=v.dtype, pin_memory=True)
+                    h.copy_(v[0] if v.dim() == 4 else v, non_blocking=True)
+                    host[k] = h
+            inflight.append(out)     # the device planes must outlive their copies
+            if "tex_fg_fine" not in host:
+                host["tex_fg_fine"] = host["tex_fg"]
+            frames.append(host)
+        side.synchronize()
+        net.marcher().check_health()
+        return frames
+
     # ---- one pass (reference src/model.py:942-1108) ----------------------------------------------
     @staticmethod
     def batch_render_pifu_nerf(net, img_in, cam_in, n_views, cam_tar, level=2, stride=0, tar_img=None, feat_geo=None,

@@ -502,6 +502,34 @@ def test_encoders_feed_the_kernels_in_place():
         torch.backends.cudnn.allow_tf32 = prev
 
 
+def test_camera_sweep_equals_per_camera_calls():
+    """render_views (one source set, many cameras; async device-to-host copies on a side stream, one sync) returns exactly what
+    per-camera render_pifu_nerf calls return, and binds / encodes the source set once."""
+    scene = syn.make_scene(src_size=128, n_kpt=18, fg_mode="hull")
+    weights = syn.make_weights(18)
+    net = build_model(weights, 18, "cuda:0")
+    a = scene_tensors(scene, syn.make_target(64, zoom=2.0), "cuda:0")
+    cams = []
+    for az in (0.3, 1.0, 2.2, 3.9, 5.1):
+        t = syn.make_target(64, az, zoom=2.0)
+        cams.append({"K": torch.from_numpy(t["K"]).cuda(), "RT": torch.from_numpy(t["RT"]).cuda(), "width": 64, "height": 64,
+                     "znear": 2.0, "zfar": 5.0, "nml_scale": 100.0})
+    cfg = dict(sample_per_ray_c=24, sample_per_ray_f=16, fine=True, uniform=True, src_foreground_mask=a["fg"], bounds=a["bounds"],
+               mask_at_box=None)
+    with torch.no_grad():
+        sweep = net.render_views(net, a["img"], a["cam"], cams, sp_data=a["sp_data"], **cfg)
+        launches = net.marcher().stats()["kernel_launches"]
+        solo = [net.render_pifu_nerf(net, a["img"], a["cam"], c, level=1, sp_data=a["sp_data"], **cfg) for c in cams]
+    assert len(sweep) == 5
+    for f, g in zip(sweep, solo):
+        for k in ("tex_fg", "alpha", "depth", "tex_fg_fine", "alpha_fine", "sdf"):
+            assert not f[k].is_cuda and torch.equal(f[k], g[k]), k
+    assert float(sweep[1]["alpha_fine"].max()) > 0.05
+    part = net.render_views(net, a["img"], a["cam"], cams, sp_data=a["sp_data"], rank=1, world=2, **cfg)
+    assert len(part) == 2 and torch.equal(part[0]["tex_fg_fine"], solo[1]["tex_fg_fine"]) and torch.equal(part[1]["tex_fg"], solo[3]["tex_fg"])
+    assert launches > 0
+
+
 def test_multi_gpu_equals_single_gpu():
     """BASELINE configs 4 and 5 on 2 GPUs (NCCL): the lattice-sharded frame and the gathered views are bit-identical to the
     single-GPU renders.  Needs >= 2 devices (skipped on the single-GPU test box; run with `gpurun --gpus 2`)."""

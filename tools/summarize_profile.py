@@ -85,8 +85,35 @@ def ncu_kernel(name, kern_sub, fn_name):
     return traffic
 
 
+def frame_dram():
+    """DRAM bytes + duration of every kernel of ONE frame (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum)."""
+    path = os.path.join(G, f"{tag}_frame_dram.csv")
+    if not os.path.exists(path):
+        return {}
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr, out = None, collections.OrderedDict()
+    for r in rows:
+        if r[0] == "ID":
+            hdr = r
+            continue
+        if hdr is None:
+            continue
+        d = dict(zip(hdr, r))
+        k = re.sub(r"\(.*", "", d["Kernel Name"]).replace("void ", "").split("::")[-1] + "#" + d["ID"]
+        v = float(d["Metric Value"].replace(",", ""))
+        u = d["Metric Unit"]
+        v *= {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}.get(u, 1)
+        out.setdefault(k, {})[d["Metric Name"]] = v
+    return out
+
+
 launches()
 tr = {"geo": ncu_kernel("geo", "shade_geo_kernelILi18", "geo_tile"), "color": ncu_kernel("color", "shade_color_kernelILi18", "color_tile")}
-json.dump({"source": f"ncu --set full capture gpurun_out/{tag}_*.ncu-rep (one launch each; a launch covers one chunk = the whole 512x512x128 frame at the default chunk size)", "kernels": tr},
+fr = frame_dram()
+tot = sum(v.get("dram__bytes_read.sum", 0) + v.get("dram__bytes_write.sum", 0) for v in fr.values())
+json.dump({"source": f"ncu captures gpurun_out/{tag}_*: `kernels` = one --set full launch of each shading kernel (a launch covers one chunk = the whole "
+                     "512x512x128 frame at the default chunk size); `frame` = every kernel of one frame (scene re-layout, front, geometry, colour list, "
+                     "colour, compositing) with --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",
+           "kernels": tr, "frame": fr, "frame_dram_bytes": tot},
           open(os.path.join(P, f"{outp}_traffic.json"), "w"), indent=1)
-print(json.dumps(tr, indent=1))
+print(json.dumps(tr, indent=1), "frame DRAM bytes", tot)
