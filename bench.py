@@ -176,7 +176,7 @@ def cpu_port_rays_per_s(cfg: dict, scene_kind: str, steps: int, warmup: int, bud
     return rays * len(times) / sum(times), cores, sum(times) / len(times) * 1e3, rays
 
 
-def run_reference_arm(args, cfg):
+def run_reference_arm(args, cfg, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -192,11 +192,24 @@ def run_reference_arm(args, cfg):
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(out_fd, line)
     return 0
 
 
+def _private_stdout():
+    """The contract is ONE JSON line on stdout: libraries (NCCL prints its version banner there) get stderr instead."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(fd: int, line: dict):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    out_fd = _private_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -213,7 +226,7 @@ def main():
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        return run_reference_arm(args, cfg)
+        return run_reference_arm(args, cfg, out_fd)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -393,7 +406,7 @@ def main():
                 "per_rank": [{n: (float(v) / args.steps if n.endswith("ms") else float(v)) for n, v in zip(names, row)}
                              for row in per_rank],
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
+        _emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
     return 0
