@@ -162,8 +162,11 @@ __device__ __forceinline__ void encode_fast(const SceneS& S, int v, int k, const
   float dx = c[0] - kc.x, dy = c[1] - kc.y, dzc = c[2] - kc.z;
   float dz = S.sp_scale * dzc;
   float w = __expf(-(dx * dx + dy * dy + dzc * dzc) * S.inv2sig2);
+  // sin/cos(pi * dz) have period 2 in dz: reduce to [-1, 1] first, so that the fast intrinsic stays accurate for any scale of the
+  // scene (sp_args.sigma = 150 / millimetre scenes make |dz| large; with metres and sigma = 0.1 the reduction is the identity)
+  const float dr = fmaf(-2.0f, rintf(0.5f * dz), dz);
   float s, co;
-  __sincosf(dz * 3.14159265358979f, &s, &co);
+  __sincosf(dr * 3.14159265358979f, &s, &co);
   float s2 = 2.0f * s * co, c2 = 1.0f - 2.0f * s * s;
   float s4 = 2.0f * s2 * c2, c4 = 1.0f - 2.0f * s2 * s2;
   e[0] = dz * w; e[1] = s * w; e[2] = co * w; e[3] = s2 * w; e[4] = c2 * w; e[5] = s4 * w; e[6] = c4 * w;

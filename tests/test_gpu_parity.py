@@ -502,6 +502,62 @@ def test_encoders_feed_the_kernels_in_place():
         torch.backends.cudnn.allow_tf32 = prev
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_odd_sizes_against_oracle(engine):
+    """Sizes that are multiples of nothing: 37 coarse + 53 fine samples, a 19 x 23 pixel lattice with step 3 / step_y 2 and offsets,
+    against the CPU oracle (coarse pointwise; fine on the oracle's own resampled depths)."""
+    scene = syn.make_scene(src_size=128, n_kpt=18, fg_mode="hull", fg_hole=True)
+    weights = syn.make_weights(18)
+    target = syn.make_target(size=96, azimuth=0.7, zoom=1.6)
+    net = build_model(weights, 18, "cuda:0")
+    a = scene_tensors(scene, target, "cuda:0")
+    m = net._bind_scene(a["cam"], a["feat_geo"], a["feat_tex"], a["sp_data"], a["img"], a["fg"], a["bounds"])
+    nx, ny, step, step_y, x0, y0, S_c, S_f = 19, 23, 3, 2, 5, 7, 37, 53
+    ys, xs = torch.arange(ny) * step_y + y0, torch.arange(nx) * step + x0
+    yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+    pix = torch.stack([xx, yy], -1).reshape(-1, 2).float()
+    ref = O.render_pixels(scene, O.fold_weights(weights), target, pix, S_c, S_f, True)
+    kw = dict(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=x0, y0=y0, step=step, step_y=step_y, nx=nx, ny=ny,
+              S_c=S_c, S_f=S_f, fine=True, engine=engine)
+    r = m.render(debug=True, **kw)
+    r2 = m.render(z_fine_override=ref["z_fine"], **kw)
+    torch.cuda.synchronize()
+    t = TOL[engine]
+    img = lambda v: v.reshape(ny, nx, 3).permute(2, 0, 1).numpy()
+    rep = []
+    good = check(rep, "tex_fg", r["tex_fg"].cpu().numpy(), img(ref["tex_fg"]), ALL, t["rgb"])
+    good &= check(rep, "contrib", r["contrib"].cpu().numpy(), ref["contrib"].numpy(), ALL, t["contrib"])
+    good &= check(rep, "tex_fg_fine@oracle-z", r2["tex_fg_fine"].cpu().numpy(), img(ref["tex_fg_fine"]), ALL, t["rgb"])
+    good &= check(rep, "alpha_fine@oracle-z", r2["alpha_fine"].cpu().numpy(), ref["alpha_fine"].reshape(ny, nx).numpy(), ALL, t["alpha"])
+    dz = (r["z_fine"].cpu() - ref["z_fine"]).abs()
+    print(f"odd sizes engine {engine}: " + "; ".join(rep) + f"; z_fine q99 {float(torch.quantile(dz.flatten(), 0.99)):.2e}")
+    assert good and float(ref["alpha"].max()) > 0.05 and float(torch.quantile(dz.flatten(), 0.99)) < 1e-3, rep
+
+
+def test_config3_early_ray_termination_on_the_bench_scene():
+    """BASELINE config 3 as benched (512 x 512, 64 + 64 samples, ert_eps = 1e-4, bench scene): every output stays within ert_eps
+    (+ round-off) of the exact render of the same engine; the coarse image pointwise, the fine image (resampled from slightly
+    different coarse weights) by quantile."""
+    scene = syn.make_scene(src_size=512, n_kpt=18)
+    weights = syn.make_weights(18)
+    target = syn.make_target(size=512)
+    net = build_model(weights, 18, "cuda:0")
+    a = scene_tensors(scene, target, "cuda:0")
+    m = net._bind_scene(a["cam"], a["feat_geo"], a["feat_tex"], a["sp_data"], a["img"], a["fg"], a["bounds"])
+    kw = dict(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=512, ny=512, S_c=64, S_f=64, fine=True)
+    exact = m.render(**kw)
+    n_exact = m.stats()["samples_valid"]
+    ert = m.render(ert_eps=1e-4, **kw)
+    n_ert = m.stats()["samples_valid"]
+    torch.cuda.synchronize()
+    d_c = float((ert["tex_fg"] - exact["tex_fg"]).abs().max())
+    d_a = float((ert["alpha"] - exact["alpha"]).abs().max())
+    q = float(torch.quantile((ert["tex_fg_fine"] - exact["tex_fg_fine"]).abs().amax(0).flatten()[::4].float(), 0.999))
+    print(f"config 3 ERT 1e-4: coarse rgb diff {d_c:.2e} alpha diff {d_a:.2e}; fine rgb q99.9 {q:.2e}; shaded samples {n_ert}/{n_exact} "
+          f"({n_ert / n_exact:.4f})")
+    assert d_c <= 1.05e-4 + 1e-5 and d_a <= 1.05e-4 + 1e-5 and q <= 2e-3 and n_ert <= n_exact
+
+
 def test_camera_sweep_equals_per_camera_calls():
     """render_views (one source set, many cameras; async device-to-host copies on a side stream, one sync) returns exactly what
     per-camera render_pifu_nerf calls return, and binds / encodes the source set once."""
