@@ -371,6 +371,7 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
   KPN_CUDA(c, cudaMemcpyAsync(c->d_raw_scene->bounds, s->bounds, sizeof(float) * 6, kind, st));
   KPN_CUDA(c, launch_prep_scene(c->d_raw_scene, c->d_scene, st));
   c->launches++;
+  if (s->fg) { KPN_CUDA(c, launch_fg_box(c->d_scene, V, st)); c->launches++; }
   c->have_scene = true;
   c->scene_views = V;
   return KPN_OK;
@@ -489,7 +490,7 @@ extern "C" int kpn_render(kpn_ctx* c, const kpn_target* tg, const kpn_opts* op, 
   ht.znear = tg->znear; ht.zfar = tg->zfar; ht.x0 = tg->x0; ht.y0 = tg->y0; ht.step = tg->step; ht.nx = tg->nx; ht.ny = tg->ny;
   ht.step_y = tg->step_y > 0 ? tg->step_y : tg->step;
   KPN_CUDA(c, cudaMemcpyAsync(c->d_target, &ht, sizeof(ht), cudaMemcpyHostToDevice, st));
-  KPN_CUDA(c, launch_prep_target(c->d_raw_target, c->d_target, st));
+  KPN_CUDA(c, launch_prep_target(c->d_raw_target, c->d_target, c->d_scene, st));
   c->launches++;
   const float* d_o = reinterpret_cast<const float*>(reinterpret_cast<const char*>(c->d_target) + offsetof(DevTarget, o));
 

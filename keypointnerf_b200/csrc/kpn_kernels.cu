@@ -9,6 +9,7 @@
 //   shade_simt     per-sample gather + keypoint encoding + MLPs for tiles of 64 valid samples
 //   composite      alpha compositing along the ray over the compact per-sample records
 //   resample       inverse-CDF resampling + merge with the coarse depths (warp per ray)
+#include <algorithm>
 #include <atomic>
 #include "kpn_device.cuh"
 #include "kpn_launch.h"
@@ -70,10 +71,57 @@ __global__ void prep_scene_kernel(const RawScene* __restrict__ raw, DevScene* sc
     }
   }
   for (int i = 0; i < 3; ++i) { sc->bounds[i] = raw->bounds[i] - 0.01f; sc->bounds[3 + i] = raw->bounds[3 + i] + 0.01f; }
+  for (int v = 0; v < MAXV; ++v) { sc->fgbox[v][0] = 1 << 30; sc->fgbox[v][1] = -1; sc->fgbox[v][2] = 1 << 30; sc->fgbox[v][3] = -1; }
 }
 
-__global__ void prep_target_kernel(const RawTarget* __restrict__ raw, DevTarget* tg) {
+// Bounding box of the non-zero foreground texels of every view (grid: 64 row slices x V views; block reduce, 4 global atomics).
+__global__ void __launch_bounds__(256)
+fg_box_kernel(DevScene* sc) {
+  const int v = blockIdx.y;
+  const int W = sc->fg.W, H = sc->fg.H;
+  const uint8_t* b = (const uint8_t*)sc->fg.ptr + (size_t)v * W * H;
+  int x0 = 1 << 30, x1 = -1, y0 = 1 << 30, y1 = -1;
+  for (int y = blockIdx.x; y < H; y += gridDim.x) {
+    const uint8_t* row = b + (size_t)y * W;
+    bool any = false;
+    for (int x = threadIdx.x; x < W; x += blockDim.x)
+      if (row[x]) { x0 = min(x0, x); x1 = max(x1, x); any = true; }
+    if (any) { y0 = min(y0, y); y1 = max(y1, y); }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, d)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, d));
+    y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, d)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, d));
+  }
+  if ((threadIdx.x & 31) == 0 && x1 >= 0) {
+    atomicMin(&sc->fgbox[v][0], x0); atomicMax(&sc->fgbox[v][1], x1); atomicMin(&sc->fgbox[v][2], y0); atomicMax(&sc->fgbox[v][3], y1);
+  }
+}
+
+// Per-view window of normalised image coordinates outside of which no sample can be valid: the frustum test's +-1.01
+// (reference src/model.py:725-729) intersected with the foreground bounding box dilated by the bilinear footprint (a look-up
+// > 0.1 needs a non-zero texel among its 4 taps, reference src/model.py:737-739) plus 1.5 texels of slack for round-off.  A box
+// that touches a border stays open on that side: border padding clamps the look-up onto the border texel.
+__device__ void fg_windows(const DevScene& sc, float win[MAXV][4]) {
+  const float lo = -1.0f - 1e-2f, hi = 1.0f + 1e-2f;
+  for (int v = 0; v < sc.V; ++v) {
+    float* w = win[v];
+    w[0] = lo; w[1] = hi; w[2] = lo; w[3] = hi;
+    if (!sc.use_fg) continue;
+    const int W = sc.fg.W, H = sc.fg.H;
+    const int* bx = sc.fgbox[v];
+    if (bx[1] < 0) { w[0] = 2.0f; w[1] = -2.0f; w[2] = 2.0f; w[3] = -2.0f; continue; }   // empty mask: nothing is valid
+    const float slack = 2.5f;   // 1 texel of bilinear footprint + 1.5 of round-off slack
+    if (bx[0] > 0 && W > 1) w[0] = fmaxf(lo, 2.0f * ((float)bx[0] - slack) / (float)(W - 1) - 1.0f);
+    if (bx[1] < W - 1 && W > 1) w[1] = fminf(hi, 2.0f * ((float)bx[1] + slack) / (float)(W - 1) - 1.0f);
+    if (bx[2] > 0 && H > 1) w[2] = fmaxf(lo, 2.0f * ((float)bx[2] - slack) / (float)(H - 1) - 1.0f);
+    if (bx[3] < H - 1 && H > 1) w[3] = fminf(hi, 2.0f * ((float)bx[3] + slack) / (float)(H - 1) - 1.0f);
+  }
+}
+
+__global__ void prep_target_kernel(const RawTarget* __restrict__ raw, DevTarget* tg, const DevScene* __restrict__ sc) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  fg_windows(*sc, tg->win);
   double a[9], inv[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) a[i * 3 + j] = (double)raw->K[i * 4 + j];
@@ -144,74 +192,175 @@ __device__ __forceinline__ void ray_for_pixel(const DevScene& sc, const DevTarge
 // exactly that range, and nothing is ever written for the invalid samples.
 // Early-ray termination (ert.s_hi > 0): only samples s_lo <= s < s_hi are looked at; a ray whose accumulated alpha of the
 // earlier segment leaves a transmittance < ert.eps contributes no entries (what it could still add is < eps per channel).
-constexpr int FRONT_WARPS = 8;
-constexpr int FRONT_MAXW = 40;   // ballot words per ray: up to 1280 samples (256 coarse + 1024 fine)
+// Depth interval [zlo, zhi] of a ray outside of which no sample can be valid: every view contributes the half-lines
+// c0 + z c1 >= 0 of "depth >= znear" and of its window's four sides (h = P (o + z d) is linear in z; h_z > 0 wherever the
+// first one holds, so the sides multiply through).  Conservative: the windows carry slack, znear a margin; samples inside the
+// interval still take the exact test.
+__device__ __forceinline__ void ray_interval(const DevScene& sc, const DevTarget& tg, const float o[3], const float d[3], float& zlo,
+                                             float& zhi) {
+  zlo = -3.0e38f; zhi = 3.0e38f;
+  if (sc.znear - 1e-3f <= 0.0f) return;   // the sides below assume a positive camera depth wherever "depth >= znear" holds
+  bool empty = false;
+  auto side = [&](float c0, float c1) {
+    if (c1 > 0.0f) zlo = fmaxf(zlo, -c0 / c1);
+    else if (c1 < 0.0f) zhi = fminf(zhi, -c0 / c1);
+    else if (c0 < 0.0f) empty = true;
+  };
+  for (int v = 0; v < sc.V; ++v) {
+    const float* P = sc.P[v];
+    float a[3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      a[i] = P[4 * i] * o[0] + P[4 * i + 1] * o[1] + P[4 * i + 2] * o[2] + P[4 * i + 3];
+      b[i] = P[4 * i] * d[0] + P[4 * i + 1] * d[1] + P[4 * i + 2] * d[2];
+    }
+    const float sl = 1e-3f * (fabsf(a[2]) + fabsf(b[2]) * 8.0f + 1.0f);   // absolute slack on the linear forms
+    side(a[2] - (sc.znear - 1e-3f), b[2]);
+    const float xl = (tg.win[v][0] + 1.0f) * 0.5f * sc.wm1, xh = (tg.win[v][1] + 1.0f) * 0.5f * sc.wm1;
+    const float yl = (tg.win[v][2] + 1.0f) * 0.5f * sc.hm1, yh = (tg.win[v][3] + 1.0f) * 0.5f * sc.hm1;
+    if (xl > xh || yl > yh) empty = true;
+    side(a[0] - xl * a[2] + sl * fmaxf(1.0f, fabsf(xl)), b[0] - xl * b[2]);
+    side(xh * a[2] - a[0] + sl * fmaxf(1.0f, fabsf(xh)), xh * b[2] - b[0]);
+    side(a[1] - yl * a[2] + sl * fmaxf(1.0f, fabsf(yl)), b[1] - yl * b[2]);
+    side(yh * a[2] - a[1] + sl * fmaxf(1.0f, fabsf(yh)), yh * b[2] - b[1]);
+  }
+  if (empty) { zlo = 3.0e38f; zhi = -3.0e38f; }
+  else { const float m = 1e-4f * (1.0f + fabsf(zlo) + fabsf(zhi)); zlo -= m; zhi += m; }   // round-off of the divisions
+}
 
-__global__ void __launch_bounds__(FRONT_WARPS * 32, 6)
+constexpr int FRONT_WARPS = 8;
+constexpr int FRONT_THREADS = FRONT_WARPS * 32;
+constexpr int FRONT_MASKW = 2048;   // ballot words of one batch of rays held in shared memory (8 KB)
+constexpr int FRONT_MAXW = 40;      // ballot words per ray: up to 1280 samples (256 coarse + 1024 fine)
+
+struct FrontRay { float d[3], n, f, zlo, zhi; int wa, wb; };   // per ray of a batch: direction, near/far, interval, word range
+
+__global__ void __launch_bounds__(FRONT_THREADS, 4)
 front_kernel(const DevScene* __restrict__ scp, const DevTarget* __restrict__ tgp, int r0, int nr, int S,
              const float* __restrict__ zbuf, float* __restrict__ ray_d, float* __restrict__ ray_nf,
              int* __restrict__ list, int list_base, int* __restrict__ counter, int* __restrict__ ray_start,
              int* __restrict__ ray_cnt, ErtSegment ert) {
   const DevScene& sc = *scp;
-  __shared__ unsigned s_mask[FRONT_WARPS][FRONT_MAXW];
-  __shared__ int s_cnt[FRONT_WARPS];
+  const DevTarget& tg = *tgp;
+  __shared__ FrontRay s_ray[FRONT_THREADS];
+  __shared__ unsigned s_mask[FRONT_MASKW];
+  __shared__ int s_cnt[FRONT_THREADS];     // per ray: valid samples, then (after the scan) exclusive offset inside the batch
+  __shared__ int s_wsum[FRONT_WARPS];
   __shared__ int s_base;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nwords = (S + 31) >> 5;
+  // rays per batch: as many as a block has threads, fewer when their ballot words would not fit (very long rays)
+  const int batch = min(FRONT_THREADS, (FRONT_MASKW / nwords) & ~31);
   const int s_lo = ert.s_hi > 0 ? ert.s_lo : 0, s_hi = ert.s_hi > 0 ? ert.s_hi : S;
-  for (int base = blockIdx.x * FRONT_WARPS; base < nr; base += gridDim.x * FRONT_WARPS) {   // block-uniform trip count
-    const int i = base + wid;
-    int cnt = 0;
-    if (i < nr) {
-      float d[3], n_r, f_r;
-      if (zbuf == nullptr) {
-        const DevTarget& tg = *tgp;
-        const int r = r0 + i;
-        const int ix = r % tg.nx, iy = r / tg.nx;
-        ray_for_pixel(sc, tg, (float)(tg.x0 + tg.step * ix), (float)(tg.y0 + tg.step_y * iy), d, n_r, f_r);
-        if (lane == 0) {
-          ray_d[3 * i + 0] = d[0]; ray_d[3 * i + 1] = d[1]; ray_d[3 * i + 2] = d[2];
-          ray_nf[2 * i + 0] = n_r; ray_nf[2 * i + 1] = f_r;
+  const float o0 = tg.o[0], o1 = tg.o[1], o2 = tg.o[2];
+  for (int base = blockIdx.x * batch; base < nr; base += gridDim.x * batch) {   // block-uniform trip count
+    // ---- phase A, one THREAD per ray: the ray, its near/far, the depth interval outside of which nothing can be valid, and the
+    //      range of 32-sample words that can intersect it (uniform depths are monotone in the sample index)
+    if (threadIdx.x < batch) {
+      const int i = base + threadIdx.x;
+      FrontRay fr;
+      fr.wa = 0; fr.wb = 0;
+      if (i < nr) {
+        if (zbuf == nullptr) {
+          const int r = r0 + i;
+          const int ix = r % tg.nx, iy = r / tg.nx;
+          ray_for_pixel(sc, tg, (float)(tg.x0 + tg.step * ix), (float)(tg.y0 + tg.step_y * iy), fr.d, fr.n, fr.f);
+          ray_d[3 * i + 0] = fr.d[0]; ray_d[3 * i + 1] = fr.d[1]; ray_d[3 * i + 2] = fr.d[2];
+          ray_nf[2 * i + 0] = fr.n; ray_nf[2 * i + 1] = fr.f;
+        } else {
+          fr.d[0] = ray_d[3 * i + 0]; fr.d[1] = ray_d[3 * i + 1]; fr.d[2] = ray_d[3 * i + 2];
+          fr.n = 0.0f; fr.f = 0.0f;
         }
-      } else {
-        d[0] = ray_d[3 * i + 0]; d[1] = ray_d[3 * i + 1]; d[2] = ray_d[3 * i + 2];
-        n_r = 0.0f; f_r = 0.0f;
-      }
-      const float o0 = tgp->o[0], o1 = tgp->o[1], o2 = tgp->o[2];
-      const bool dead = ert.ray_alpha != nullptr && 1.0f - ert.ray_alpha[i] < ert.eps;   // ray already opaque
-      for (int w = 0; w < nwords; ++w) {
-        const int s = 32 * w + lane;
-        bool ok = false;
-        if (s < S && s >= s_lo && s < s_hi && !dead) {
-          const float z = zbuf ? zbuf[(long long)i * S + s] : coarse_depth(n_r, f_r, s, S);
-          const float p[3] = {o0 + d[0] * z, o1 + d[1] * z, o2 + d[2] * z};   // reference src/model.py:1057
-          Proj q[MAXV];
-          ok = sample_valid(sc, p, q);
+        const float oo[3] = {o0, o1, o2};
+        ray_interval(sc, tg, oo, fr.d, fr.zlo, fr.zhi);
+        const bool dead = ert.ray_alpha != nullptr && 1.0f - ert.ray_alpha[i] < ert.eps;   // ray already opaque
+        if (!dead && fr.zlo <= fr.zhi) {
+          int sa = s_lo, sb = s_hi;
+          if (zbuf == nullptr && S > 1 && fr.f != fr.n) {
+            // z(s) = n + (f - n) s / (S - 1): samples with z in [zlo, zhi] have s in [ta, tb] (one sample of slack either side)
+            const float k = (float)(S - 1) / (fr.f - fr.n);
+            float ta = (fr.zlo - fr.n) * k, tb = (fr.zhi - fr.n) * k;
+            if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+            if (ta == ta && tb == tb) {   // (NaN: a degenerate near == far up to round-off; keep the whole ray)
+              sa = max(sa, (int)fminf(fmaxf(floorf(ta) - 1.0f, 0.0f), (float)S));
+              sb = min(sb, (int)fminf(fmaxf(ceilf(tb) + 2.0f, 0.0f), (float)S));
+            }
+          }
+          if (sa < sb) { fr.wa = sa >> 5; fr.wb = (sb + 31) >> 5; }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_mask[wid][w] = m;
-        cnt += __popc(m);
       }
+      s_ray[threadIdx.x] = fr;
+      s_cnt[threadIdx.x] = 0;
     }
-    if (lane == 0) s_cnt[wid] = cnt;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
+    // ---- phase B, one WARP per ray (round robin over the batch): the exact validity test of the samples in the word range,
+    //      lane l takes samples l, l+32, ..; ballots -> the ray's valid samples in order
+    for (int t = wid; t < batch; t += FRONT_WARPS) {
+      const FrontRay& fr = s_ray[t];
+      const int i = base + t;
+      unsigned* mw = s_mask + t * nwords;
+      int cnt = 0;
+      for (int w = 0; w < nwords; ++w) {
+        unsigned m = 0u;
+        if (w >= fr.wa && w < fr.wb) {
+          const int s = 32 * w + lane;
+          bool ok = false;
+          if (s < S && s >= s_lo && s < s_hi) {
+            const float z = zbuf ? zbuf[(long long)i * S + s] : coarse_depth(fr.n, fr.f, s, S);
+            if (z >= fr.zlo && z <= fr.zhi) {   // outside the ray's interval no view can accept the sample
+              const float p[3] = {o0 + fr.d[0] * z, o1 + fr.d[1] * z, o2 + fr.d[2] * z};   // reference src/model.py:1057
+              Proj q[MAXV];
+              ok = sample_valid(sc, p, q);
+            }
+          }
+          m = __ballot_sync(0xffffffffu, ok);
+          cnt += __popc(m);
+        }
+        if (lane == 0) mw[w] = m;
+      }
+      if (lane == 0) s_cnt[t] = cnt;
+    }
+    __syncthreads();
+    // ---- block scan of the batch's per-ray counts, ONE atomic reserves the batch's contiguous range of the work list
+    {
+      const int c = threadIdx.x < batch ? s_cnt[threadIdx.x] : 0;
+      int v = c;
 #pragma unroll
-      for (int w = 0; w < FRONT_WARPS; ++w) { const int c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
-      s_base = tot ? atomicAdd(counter, tot) : 0;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += u;
+      }
+      if (lane == 31) s_wsum[wid] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < FRONT_WARPS; ++w) { const int x = s_wsum[w]; s_wsum[w] = tot; tot += x; }
+        s_base = tot ? atomicAdd(counter, tot) : 0;
+      }
+      __syncthreads();
+      if (threadIdx.x < batch) {
+        const int off = s_wsum[wid] + v - c;   // exclusive offset of this ray inside the batch
+        s_cnt[threadIdx.x] = off;
+        const int i = base + threadIdx.x;
+        if (i < nr) { ray_start[i] = list_base + s_base + off; ray_cnt[i] = c; }
+      }
     }
     __syncthreads();
-    if (i < nr) {
-      int pos = list_base + s_base + s_cnt[wid];
-      if (lane == 0) { ray_start[i] = pos; ray_cnt[i] = cnt; }
-      for (int w = 0; w < nwords; ++w) {
-        const unsigned m = s_mask[wid][w];
+    // ---- the entries, ordered by (ray, sample)
+    for (int t = wid; t < batch; t += FRONT_WARPS) {
+      const int i = base + t;
+      if (i >= nr) break;
+      const FrontRay& fr = s_ray[t];
+      const unsigned* mw = s_mask + t * nwords;
+      int pos = list_base + s_base + s_cnt[t];
+      for (int w = fr.wa; w < fr.wb; ++w) {
+        const unsigned m = mw[w];
         if ((m >> lane) & 1u) list[pos + __popc(m & ((1u << lane) - 1u))] = i * S + 32 * w + lane;
         pos += __popc(m);
       }
     }
-    __syncthreads();   // s_cnt / s_base / s_mask are rewritten by the next iteration
+    __syncthreads();   // the shared arrays are rewritten by the next batch
   }
 }
 
@@ -778,8 +927,12 @@ cudaError_t launch_prep_scene(const RawScene* raw, DevScene* sc, cudaStream_t st
   prep_scene_kernel<<<1, 32, 0, st>>>(raw, sc);
   return cudaGetLastError();
 }
-cudaError_t launch_prep_target(const RawTarget* raw, DevTarget* tg, cudaStream_t st) {
-  prep_target_kernel<<<1, 32, 0, st>>>(raw, tg);
+cudaError_t launch_fg_box(DevScene* sc, int n_views, cudaStream_t st) {
+  fg_box_kernel<<<dim3(64, n_views), 256, 0, st>>>(sc);
+  return cudaGetLastError();
+}
+cudaError_t launch_prep_target(const RawTarget* raw, DevTarget* tg, const DevScene* sc, cudaStream_t st) {
+  prep_target_kernel<<<1, 32, 0, st>>>(raw, tg, sc);
   return cudaGetLastError();
 }
 cudaError_t launch_front(const DevScene* sc, const DevTarget* tg, int r0, int nr, int S, const float* zbuf, float* ray_d,
@@ -789,13 +942,15 @@ cudaError_t launch_front(const DevScene* sc, const DevTarget* tg, int r0, int nr
   static std::atomic<int> per_sm{0};
   int bps = per_sm.load(std::memory_order_acquire);
   if (bps == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, front_kernel, FRONT_WARPS * 32, 0) != cudaSuccess || bps < 1) bps = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, front_kernel, FRONT_THREADS, 0) != cudaSuccess || bps < 1) bps = 4;
     per_sm.store(bps, std::memory_order_release);
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  front_kernel<<<grid_for(nr, FRONT_WARPS, sms * bps), FRONT_WARPS * 32, 0, st>>>(sc, tg, r0, nr, S, zbuf, ray_d, ray_nf, list, list_base,
+  const int nwords = (S + 31) / 32;
+  const int batch = std::min(FRONT_THREADS, (FRONT_MASKW / nwords) & ~31);
+  front_kernel<<<grid_for(nr, batch, sms * bps), FRONT_THREADS, 0, st>>>(sc, tg, r0, nr, S, zbuf, ray_d, ray_nf, list, list_base,
                                                                             counter, ray_start, ray_cnt, ert);
   return cudaGetLastError();
 }

@@ -7,7 +7,8 @@ namespace kpn {
 
 cudaError_t launch_pack_nhwc_f32(const float* in, float* out, int V, int C, int H, int W, int Cp, cudaStream_t st);
 cudaError_t launch_prep_scene(const RawScene* raw, DevScene* sc, cudaStream_t st);
-cudaError_t launch_prep_target(const RawTarget* raw, DevTarget* tg, cudaStream_t st);
+cudaError_t launch_fg_box(DevScene* sc, int n_views, cudaStream_t st);
+cudaError_t launch_prep_target(const RawTarget* raw, DevTarget* tg, const DevScene* sc, cudaStream_t st);
 cudaError_t launch_front(const DevScene* sc, const DevTarget* tg, int r0, int nr, int S, const float* zbuf, float* ray_d,
                          float* ray_nf, int* list, int list_base, int* counter, int* ray_start, int* ray_cnt, const ErtSegment& ert,
                          cudaStream_t st);

@@ -43,6 +43,7 @@ struct DevScene {
   float C[MAXV][3];        // source camera centres (inverse(KRT)[:3,3], src/model.py:823-824)
   float kc[MAXV][MAXK][3]; // keypoints in each source camera frame (src/spatial.py:85)
   float bounds[6];         // padded by (-0.01,+0.01) (src/model.py:1193)
+  int fgbox[MAXV][4];      // per view [x0, x1, y0, y1]: bounding box of the non-zero foreground texels (x1 < 0: none)
   float sp_scale, inv2sig2;
   int sp_level;
   float freq[MAX_SPL];     // float32(pi * 2^l) (src/spatial.py:41-47)
@@ -56,6 +57,8 @@ struct DevTarget {
   float znear, zfar;
   int x0, y0, step, nx, ny;
   int step_y;              // lattice step along y (== step for the reference's square lattices)
+  float win[MAXV][4];      // per source view [u_lo, u_hi, v_lo, v_hi]: a sample whose normalised projection lies outside can not be
+                           // valid (frustum +-1.01 intersected with the dilated foreground bounding box); conservative
 };
 
 // Packed dense layers for the fp32 SIMT engine: Wt [K][ldw] transposed, zero padded to ldw = roundup(N,32).

@@ -558,6 +558,37 @@ def test_config3_early_ray_termination_on_the_bench_scene():
     assert d_c <= 1.05e-4 + 1e-5 and d_a <= 1.05e-4 + 1e-5 and q <= 2e-3 and n_ert <= n_exact
 
 
+def test_front_kernel_validity_is_exact():
+    """The front kernel skips, per ray, every sample outside a conservative depth interval (frustum + foreground bounding box of
+    every view) and takes the exact test inside it: the number of valid samples must equal the oracle's count EXACTLY, for
+    all-foreground, silhouette and holed masks (incl. masks touching the image border), zoomed / wide / off-axis targets and
+    the fine pass' resampled depths."""
+    weights = syn.make_weights(18)
+    net = build_model(weights, 18, "cuda:0")
+    cases = [dict(fg_mode="ones", fg_hole=False, size=48, az=1.0, zoom=1.0), dict(fg_mode="hull", fg_hole=False, size=64, az=2.0, zoom=1.5),
+             dict(fg_mode="hull", fg_hole=True, size=40, az=0.3, zoom=3.0), dict(fg_mode="ones", fg_hole=True, size=56, az=4.4, zoom=0.6)]
+    for c in cases:
+        scene = syn.make_scene(src_size=128, n_kpt=18, fg_mode=c["fg_mode"], fg_hole=c["fg_hole"])
+        target = syn.make_target(size=c["size"], azimuth=c["az"], zoom=c["zoom"])
+        a = scene_tensors(scene, target, "cuda:0")
+        m = net._bind_scene(a["cam"], a["feat_geo"], a["feat_tex"], a["sp_data"], a["img"], a["fg"], a["bounds"])
+        n, S_c, S_f = c["size"], 24, 16
+        r = m.render(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=n, ny=n, S_c=S_c, S_f=S_f,
+                     fine=True, engine=1, debug=True)
+        got = m.stats()["samples_valid"]
+        pix = O.pixel_lattice(n, n, 1, 0, 0)
+        o, d, n_r, f_r = O.ray_setup(pix, target["K"], target["RT"], 2.0, 5.0)
+        near, far, hit = O.ray_bbox(scene["bounds"], o, d)
+        n_r, f_r = O.clip_near_far(n_r, f_r, near, far, hit)
+        want = 0
+        for zz in (O.coarse_z(n_r, f_r, S_c), r["z_fine"].cpu()):   # the fine pass tests the GPU's own merged depths
+            P = (o[:, None, :] + d[:, None, :] * zz[..., None]).reshape(-1, 3)
+            xy, zc = O.project(scene, P)
+            want += int(O.validity(scene, xy, zc).sum())
+        print(f"front validity {c}: valid samples {got} (oracle {want})")
+        assert got == want and want > 0, c
+
+
 def test_camera_sweep_equals_per_camera_calls():
     """render_views (one source set, many cameras; async device-to-host copies on a side stream, one sync) returns exactly what
     per-camera render_pifu_nerf calls return, and binds / encodes the source set once."""
