@@ -191,6 +191,16 @@ int kpn_check_health(kpn_ctx* ctx, void* stream);
  * (cudaFree + cudaMalloc: implicit device synchronisation) the first time a larger size is seen. */
 int kpn_reserve(kpn_ctx* ctx, long long max_rays, int max_samples);
 
+/* Source-view decode on the device: what ZJUDataset.__getitem__ does to every view on CPU workers (reference
+ * src/zju_dataset.py:266-287): cv2.undistort of the image (float32 / 255) and of the mask, cv2.resize by 1 / factor (INTER_AREA /
+ * INTER_NEAREST; factor >= 1 integer, source size divisible by it), image[mask == 0] = 0.  Bit-identical to the cv2 calls.
+ *   images (V, H0, W0, 3) uint8 RGB, masks (V, H0, W0) uint8 (non-zero = foreground) or NULL,
+ *   cams   (V, 18) double per view: the 9 entries of inverse(K) row-major, then fx, fy, cx, cy, k1, k2, p1, p2, k3,
+ *   out_img (V, 3, H0/factor, W0/factor) fp32 in [0, 1], out_mask (V, 1, H0/factor, W0/factor) uint8 in {0, 1} or NULL.
+ * `mem` = kpn_mem of every pointer (host pointers are staged through the context's buffers on `stream`). */
+int kpn_decode_views(kpn_ctx* ctx, const uint8_t* images, const uint8_t* masks, const double* cams, int n_views, int src_h, int src_w,
+                     int factor, float* out_img, uint8_t* out_mask, int mem, void* stream);
+
 /* Debug: the device watchdog words of the tensor-core kernels.  Every barrier wait of those kernels gives up after ~2^20
  * suspended polls instead of hanging the GPU; out16 (host, may be NULL) receives [0] flag (!= 0: some wait gave up; results of
  * that launch are invalid), [1] block, [2] thread, [3] tag of the wait, [4] parity; [5..15] zero.  enable != 0 clears the

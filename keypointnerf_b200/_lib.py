@@ -19,7 +19,7 @@ KPN_NUM_LAYERS = 19
 KPN_NHWC_FEAT64, KPN_NHWC_FEAT8, KPN_NHWC_FEATTEX = 1, 2, 4
 
 EXPORTS = ["kpn_abi_version", "kpn_create", "kpn_destroy", "kpn_last_error", "kpn_set_weights", "kpn_set_scene",
-           "kpn_render", "kpn_query", "kpn_get_stats", "kpn_set_profiling", "kpn_selftest_umma", "kpn_selftest_umma2", "kpn_debug_timing", "kpn_debug_kmap", "kpn_check_health", "kpn_reserve", "kpn_debug_stage_times"]
+           "kpn_render", "kpn_query", "kpn_get_stats", "kpn_set_profiling", "kpn_selftest_umma", "kpn_selftest_umma2", "kpn_debug_timing", "kpn_debug_kmap", "kpn_check_health", "kpn_reserve", "kpn_debug_stage_times", "kpn_decode_views"]
 KPN_ABI_VERSION = 2
 
 c_float_p = C.POINTER(C.c_float)
@@ -91,6 +91,9 @@ def load() -> C.CDLL:
     lib.kpn_check_health.restype = C.c_int
     lib.kpn_reserve.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
     lib.kpn_reserve.restype = C.c_int
+    lib.kpn_decode_views.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p]
+    lib.kpn_decode_views.restype = C.c_int
     lib.kpn_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.kpn_create.restype = C.c_int
     lib.kpn_destroy.argtypes = [C.c_void_p]

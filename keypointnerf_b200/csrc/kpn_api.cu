@@ -720,6 +720,39 @@ extern "C" int kpn_debug_stage_times(kpn_ctx* c, unsigned long long* out, int n_
   return KPN_OK;
 }
 
+extern "C" int kpn_decode_views(kpn_ctx* c, const uint8_t* images, const uint8_t* masks, const double* cams, int n_views, int src_h,
+                                int src_w, int factor, float* out_img, uint8_t* out_mask, int mem, void* stream) {
+  if (!c || !images || !cams || !out_img) return KPN_ERR_ARG;
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_views < 1 || src_h < 1 || src_w < 1 || factor < 1 || src_h % factor || src_w % factor)
+    KPN_FAIL(c, KPN_ERR_ARG, "decode: %d views of %dx%d by 1/%d", n_views, src_h, src_w, factor);
+  if (mem != KPN_MEM_HOST && mem != KPN_MEM_DEVICE) KPN_FAIL(c, KPN_ERR_ARG, "bad mem kind");
+  const size_t npx = (size_t)n_views * src_h * src_w, nout = npx / ((size_t)factor * factor);
+  const size_t cam_bytes = (size_t)n_views * 18 * sizeof(double);
+  const uint8_t* d_img = images; const uint8_t* d_msk = masks; const void* d_cam = cams;
+  float* d_out = out_img; uint8_t* d_om = out_mask;
+  if (mem == KPN_MEM_HOST) {
+    // staging layout: cams | images | masks | out_img | out_mask
+    const size_t off_img = (cam_bytes + 255) / 256 * 256, off_msk = off_img + (npx * 3 + 255) / 256 * 256;
+    const size_t off_out = off_msk + (npx + 255) / 256 * 256, off_om = off_out + nout * 3 * sizeof(float);
+    KPN_CUDA(c, c->ws_in.reserve(off_om + nout));
+    char* b = c->ws_in.as<char>();
+    KPN_CUDA(c, cudaMemcpyAsync(b, cams, cam_bytes, cudaMemcpyHostToDevice, st));
+    KPN_CUDA(c, cudaMemcpyAsync(b + off_img, images, npx * 3, cudaMemcpyHostToDevice, st));
+    if (masks) KPN_CUDA(c, cudaMemcpyAsync(b + off_msk, masks, npx, cudaMemcpyHostToDevice, st));
+    d_cam = b; d_img = reinterpret_cast<uint8_t*>(b + off_img); d_msk = masks ? reinterpret_cast<uint8_t*>(b + off_msk) : nullptr;
+    d_out = reinterpret_cast<float*>(b + off_out); d_om = out_mask ? reinterpret_cast<uint8_t*>(b + off_om) : nullptr;
+  }
+  KPN_CUDA(c, launch_decode_views(d_img, d_msk, d_cam, n_views, src_h, src_w, factor, d_out, d_om, st));
+  c->launches++;
+  if (mem == KPN_MEM_HOST) {
+    KPN_CUDA(c, cudaMemcpyAsync(out_img, d_out, nout * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_mask) KPN_CUDA(c, cudaMemcpyAsync(out_mask, d_om, nout, cudaMemcpyDeviceToHost, st));
+  }
+  return KPN_OK;
+}
+
 extern "C" int kpn_set_profiling(kpn_ctx* c, int enable) {
   if (!c) return KPN_ERR_ARG;
   c->profiling = enable != 0;

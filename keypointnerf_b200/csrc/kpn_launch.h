@@ -38,6 +38,9 @@ cudaError_t tc_stage_times(unsigned long long* out, int n_words, int* n_tiles); 
 size_t tc_weight_blob_bytes(int n_kpt);
 size_t tc_weight_lo_bytes(int n_kpt);
 bool tc_supported(int n_views, int n_kpt, int sp_level);
+// source-view decode (kpn_decode.cu): cams = V x {double ir[9], fx, fy, cx, cy, k1, k2, p1, p2, k3} on the device
+cudaError_t launch_decode_views(const uint8_t* images, const uint8_t* masks, const void* cams, int V, int H0, int W0, int factor,
+                                float* out_img, uint8_t* out_mask, cudaStream_t st);
 int max_coarse_samples();
 int simt_max_kpt();
 

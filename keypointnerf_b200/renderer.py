@@ -220,6 +220,46 @@ class RayMarcher:
             self.check_health()
         return out, valid.bool()
 
+    # ---- source-view decode (reference ZJUDataset.__getitem__, src/zju_dataset.py:266-287) ----------
+    def decode_views(self, images: torch.Tensor, masks: torch.Tensor | None, K, D, ratio: float = 0.5):
+        """Undistort + resize + mask every source view on the device (bit-identical to the reference's cv2 calls).
+        ``images`` (V,H0,W0,3) uint8 RGB as read from disk, ``masks`` (V,H0,W0) uint8/bool (non-zero = foreground) or None,
+        ``K`` (V,3,3) and ``D`` (V,5) float32 camera matrices / distortion coefficients, ``ratio`` = 1/integer.
+        Returns ``(img (V,3,H,W) float32 in [0,1] with the background zeroed, mask (V,1,H,W) bool, K scaled by ratio)`` on the
+        device the images live on (host tensors are staged by the library on the current stream)."""
+        factor = int(round(1.0 / float(ratio)))
+        assert factor >= 1 and abs(factor * float(ratio) - 1.0) < 1e-6, "ratio must be 1 / integer"
+        images = images.detach().to(torch.uint8).contiguous()
+        V, H0, W0, _ = images.shape
+        on_dev = images.is_cuda
+        dev = images.device
+        if masks is not None:
+            masks = masks.detach().to(device=dev, dtype=torch.uint8).reshape(V, H0, W0).contiguous()
+        Kn = np.asarray(K.detach().cpu() if isinstance(K, torch.Tensor) else K, dtype=np.float32).reshape(V, 3, 3)
+        Dn = np.asarray(D.detach().cpu() if isinstance(D, torch.Tensor) else D, dtype=np.float32).reshape(V, -1)
+        cams = np.zeros((V, 18), dtype=np.float64)
+        for v in range(V):   # cv2.undistort: newCameraMatrix = K, maps computed in double from the float32 inputs
+            Kd = Kn[v].astype(np.float64)
+            cams[v, :9] = np.linalg.inv(Kd).reshape(-1)
+            cams[v, 9:13] = (Kd[0, 0], Kd[1, 1], Kd[0, 2], Kd[1, 2])
+            cams[v, 13:13 + min(5, Dn.shape[1])] = Dn[v, :5].astype(np.float64)
+        cams_t = torch.from_numpy(cams)
+        cams_t = cams_t.to(dev) if on_dev else cams_t
+        H, W = H0 // factor, W0 // factor
+        kw = dict(device=dev) if on_dev else dict(pin_memory=True)
+        img = torch.empty(V, 3, H, W, dtype=torch.float32, **kw)
+        msk = torch.empty(V, 1, H, W, dtype=torch.uint8, **kw)
+        L.check(self.lib, self.ctx,
+                self.lib.kpn_decode_views(self.ctx, images.data_ptr(), masks.data_ptr() if masks is not None else None,
+                                          cams_t.data_ptr(), V, H0, W0, factor, img.data_ptr(), msk.data_ptr(),
+                                          L.KPN_MEM_DEVICE if on_dev else L.KPN_MEM_HOST, self._stream()), "kpn_decode_views")
+        self._keep_call = [images, masks, cams_t]
+        if not on_dev:
+            torch.cuda.current_stream(self.device).synchronize()
+        K_out = torch.from_numpy(Kn.copy())
+        K_out[:, :2] = K_out[:, :2] * float(ratio)          # in_K[:2] = in_K[:2] * self.ratio  (src/zju_dataset.py:296)
+        return img, msk.bool(), K_out
+
     def stats(self) -> dict:
         st = L.KpnStats()
         L.check(self.lib, self.ctx, self.lib.kpn_get_stats(self.ctx, C.byref(st), self._stream()), "kpn_get_stats")
