@@ -10,7 +10,7 @@ from oracle import decode_oracle as DO  # checker only
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("ratio,shape", [(0.5, (256, 320)), (1.0, (128, 160)), (0.25, (256, 256))])
+@pytest.mark.parametrize("ratio,shape", [(0.5, (256, 320)), (1.0, (128, 160)), (0.25, (256, 256)), (1.0 / 3.0, (192, 240))])
 def test_decode_matches_cv2_bit_for_bit(ratio, shape):
     imgs, msks, K, D = DO.synthetic_views(3, shape[0], shape[1], seed=int(ratio * 8))
     want = [DO.decode_view(imgs[v], msks[v], K[v], D[v], ratio) for v in range(3)]
@@ -20,7 +20,7 @@ def test_decode_matches_cv2_bit_for_bit(ratio, shape):
         tm = torch.from_numpy(msks).to(dev)
         img, msk, Ks = m.decode_views(ti, tm, K, D, ratio)
         torch.cuda.synchronize()
-        assert img.shape == (3, 3, int(shape[0] * ratio), int(shape[1] * ratio)) and msk.dtype == torch.bool
+        assert img.shape == (3, 3, want[0][0].shape[1], want[0][0].shape[2]) and msk.dtype == torch.bool
         for v in range(3):
             assert np.array_equal(msk[v].cpu().numpy(), want[v][1]), (dev, v, "mask")
             d = np.abs(img[v].cpu().numpy() - want[v][0])
