@@ -235,7 +235,7 @@ __device__ __forceinline__ void geo_wait(GeoCtx& c) {
   tc::fence_after_sync();
 }
 template <int NK, int STAGE>
-__device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint32_t lo_delta, int lo_mask, uint32_t el);
+__device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t d_tm, uint32_t wlo0, uint32_t lo_delta, int lo_mask, uint32_t el);
 // issuer warp only: once every row warp of the pair has signalled this stage's input, issue its MMAs
 template <int NK, int STAGE>
 __device__ __forceinline__ void geo_mma(GeoCtx& c, bool tim_on = false, int tim_row = 0, int lane = 0) {
@@ -244,7 +244,7 @@ __device__ __forceinline__ void geo_mma(GeoCtx& c, bool tim_on = false, int tim_
     c.pha ^= 1u;
     tc::fence_after_sync();
     TIM(3 + 5 * STAGE);
-    geo_issue<NK, STAGE>(c.slot_tm, c.wlo0, c.lod, c.lo_mask, c.el);
+    geo_issue<NK, STAGE>(c.slot_tm, c.slot_tm + (uint32_t)geo_dcol(STAGE), c.wlo0, c.lod, c.lo_mask, c.el);
     tc::mma_commit2_el(c.acc_ready, c.el);
     TIM(4 + 5 * STAGE);
   }
@@ -985,7 +985,7 @@ constexpr uint32_t A_IN_R1 = 0xA9Au;
 // (a stage's half tile sits at plan offset / 2; `lo_delta` = descriptor distance of the W_lo halves).  Per K chunk of 16 the
 // descriptor's start address advances by two core-matrix columns (2 * LBO).  Order: A_hi x W_hi, [A_hi x W_lo], [A_lo x W_hi].
 template <int NK, int STAGE>
-__device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint32_t lo_delta, int lo_mask, uint32_t el) {
+__device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t d_tm, uint32_t wlo0, uint32_t lo_delta, int lo_mask, uint32_t el) {
   const bool two_term = (lo_mask >> STAGE) & 1, act_lo = STAGE >= 4 && ((lo_mask >> (STAGE + 2)) & 1);
   constexpr TcPlan plan = make_tc_plan(NK);
   constexpr int Kp = plan.st[STAGE].Kp, Np = plan.st[STAGE].Np;
@@ -998,7 +998,6 @@ __device__ __forceinline__ void geo_issue(uint32_t slot_tm, uint32_t wlo0, uint3
   constexpr int BIASCOL = STAGE == 4 ? 128 : 64;                      // column of the separate bias chunk (stages 4, 5)
   constexpr int LOCOL = STAGE == 4 ? 64 : 32;                         // first column of the A_lo half (stages 4, 5)
   const uint32_t b0 = wlo0 + ((plan.st[STAGE].off / 2u) >> 4) + ((lbo >> 4) << 16);
-  const uint32_t d_tm = slot_tm + (uint32_t)geo_dcol(STAGE);
 #pragma unroll
   for (int j = 0; j < NCH; ++j)
     tc::mma_ts2_el(d_tm, slot_tm + (uint32_t)(j < NACT ? 8 * j : BIASCOL), b0 + (uint32_t)j * step, dhi, idesc, j > 0 ? 1u : 0u, el);
@@ -1155,6 +1154,314 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// view-sequential geometry + density kernel (engine 3, 18 keypoints)
+// ------------------------------------------------------------------------------------------------------------------
+// Same network, same resident two-term weights, same CTA pairs as shade_geo_kernel, other mapping of the work onto an SM:
+//   * a tile row is a SAMPLE (128 samples per CTA, 256 per pair), not a (sample, view) pair: the three views of a sample go
+//     through stages 0-3 one after the other in the same tensor-memory lane, their 64-wide outputs X_0, X_1, X_2 stay in tensor
+//     memory, and the view pooling (reference src/utils.py:722-748) is thread-local arithmetic instead of 3-lane shuffles;
+//     the pooled stages P0|compress and P1 run once per sample instead of once per (sample, view) row;
+//   * FOUR threads per row (16 row warps = 4 lane quarters x 4 column quarters): a stage's epilogue is 32 accumulator
+//     columns per thread, every warp of the CTA works on the same stage;
+//   * one tile in flight per CTA: 14 tensor stages per tile (3 x [L0 L1 L2 L3] + P0 + P1) instead of 6 per 40 samples.
+// Tensor-memory columns (512 allocated): A [0,136) as in shade_geo_kernel's table | D [160,288) | X_0 [288,352) | X_1 [352,416)
+// | X_2 [416,480) (every access naturally aligned to its width).  L3's accumulator IS X_v.  Exchange of the four column
+// quarters' partial density sums: D columns [96,128) of the row's lane (free once the P1 accumulator has been read; rewritten
+// only by the next tile's L0).
+constexpr int VS_D = 160, VS_X = 288;
+constexpr int VS_THREADS = 16 * 32;
+
+template <int NK, int STAGE>
+__device__ __forceinline__ void vs_mma(GeoCtx& c, uint32_t d_col) {
+  if (c.issuer) {
+    tc::mbar_wait(c.a_ready, c.pha, 0x60u + (uint32_t)STAGE);
+    c.pha ^= 1u;
+    tc::fence_after_sync();
+    geo_issue<NK, STAGE>(c.slot_tm, c.slot_tm + d_col, c.wlo0, c.lod, c.lo_mask, c.el);
+    tc::mma_commit2_el(c.acc_ready, c.el);
+  }
+}
+__device__ __forceinline__ void vs_wait(GeoCtx& c) {
+  tc::mbar_wait(c.acc_ready, c.ph, 0x70u);
+  c.ph ^= 1u;
+  tc::fence_after_sync();
+}
+// epilogue of a 128-wide softplus stage, this thread's 32 accumulator columns at d -> 16 packed columns at a
+__device__ __forceinline__ void vs_epi_sp(uint32_t d, uint32_t a, bool bias_tail) {
+  uint32_t r[32];
+  tc::tmem_ld32(d, r);
+  tc::wait_ld();
+  uint32_t o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = sp_pair(r[2 * i], r[2 * i + 1]);
+  if (bias_tail) { o[12] = H2_ONE; o[13] = 0u; o[14] = 0u; o[15] = 0u; }
+  tc::tmem_st16(a, o);
+}
+
+template <int NK>
+__device__ __forceinline__ void vs_tile(const SceneS& sc, const float* __restrict__ wp2, const SampleSrc& src,
+                                        const int* __restrict__ list, int count, int tile, GeoCtx& cx, int q4, int cq, int lane,
+                                        int query_mode, const ShadeOut& so, uint4* __restrict__ lat_out) {
+  static_assert(NK == 18, "the column plan below is the 18-keypoint one (4 runs of 24 columns)");
+  const uint32_t A = cx.tm;                       // lane field = this row, column 0
+  const uint32_t D = A + (uint32_t)VS_D;
+  const int si = tile * 128 + 32 * q4 + lane;     // this row's index into the work list
+  const bool live = si < count;                   // rows past the end replay the last sample and write nothing
+  const int id = list[max(min(si, count - 1), 0)];
+  float p[3], dir[3];
+  fetch_sample(src, id, p, dir);
+  // view weights (reference src/model.py:750-759; mask == 1 for shaded samples) and the projections the gathers use
+  Proj q[3];
+  float pw[3];
+  {
+    float s = 0.0f;
+#pragma unroll
+    for (int v = 0; v < 3; ++v) { q[v] = project_s(sc, v, p); pw[v] = boundary_weight_fast(q[v]); s += pw[v]; }
+    const float inv = 1.0f / (s + 1e-6f);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) pw[v] *= inv;
+  }
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    // ---- stage 0 input of (sample, view v): this thread's run of 24 columns (tc_kmap_vseq)
+    {
+      float c[3];
+      const float* E = sc.E[v];
+      c[0] = E[0] * p[0] + E[1] * p[1] + E[2] * p[2] + E[3];
+      c[1] = E[4] * p[0] + E[5] * p[1] + E[6] * p[2] + E[7];
+      c[2] = E[8] * p[0] + E[9] * p[1] + E[10] * p[2] + E[11];
+      const Taps t64 = make_taps(q[v].u, q[v].v, sc.f64.W, sc.f64.H);
+      uint32_t a[24];
+      if (cq < 3) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float e0[7], e1[7];
+          encode_fast(sc, v, 4 * cq + 2 * j, c, e0);
+          encode_fast(sc, v, 4 * cq + 2 * j + 1, c, e1);
+#pragma unroll
+          for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
+        }
+#pragma unroll
+        for (int g = 0; g < 5; ++g) {
+          float f[4];
+          gather_f32<1>(sc.f64, v, t64, 5 * cq + g, f);
+          a[14 + 2 * g] = tc::pack_h2(f[0], f[1]);
+          a[15 + 2 * g] = tc::pack_h2(f[2], f[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float e0[7], e1[7];
+          encode_fast(sc, v, 12 + 2 * j, c, e0);
+          encode_fast(sc, v, 13 + 2 * j, c, e1);
+#pragma unroll
+          for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
+        }
+        float f[4];
+        gather_f32<1>(sc.f64, v, t64, 15, f);
+        a[21] = tc::pack_h2(f[0], f[1]);
+        a[22] = tc::pack_h2(f[2], f[3]);
+        a[23] = H2_ONE;
+      }
+      // the previous view's L3 (or the previous tile's P1) has completed: every thread waited for its accumulator
+      tc::tmem_st8(A + 24u * (uint32_t)cq, a);
+      tc::tmem_st8(A + 24u * (uint32_t)cq + 8u, a + 8);
+      tc::tmem_st8(A + 24u * (uint32_t)cq + 16u, a + 16);
+    }
+    geo_signal(cx, lane);
+    vs_mma<NK, 0>(cx, VS_D);
+    vs_wait(cx);
+    // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720)
+    vs_epi_sp(D + 32u * (uint32_t)cq, A + 16u * (uint32_t)cq, false);
+    if (cq == 0) {
+      const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tc::tmem_st8(A + 64, b);
+    }
+    geo_signal(cx, lane);
+    vs_mma<NK, 1>(cx, VS_D);
+    vs_wait(cx);
+    vs_epi_sp(D + 32u * (uint32_t)cq, A + 16u * (uint32_t)cq, false);
+    if (cq == 3) {   // [64,72): feat8 | bias | 0
+      uint32_t b[8] = {0u, 0u, 0u, 0u, H2_ONE, 0u, 0u, 0u};
+      const Taps t8 = make_taps(q[v].u, q[v].v, sc.f8.W, sc.f8.H);
+      float g8[8];
+      gather_f32<2>(sc.f8, v, t8, 0, g8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
+      tc::tmem_st8(A + 64, b);
+    }
+    geo_signal(cx, lane);
+    vs_mma<NK, 2>(cx, VS_D);
+    vs_wait(cx);
+    vs_epi_sp(D + 32u * (uint32_t)cq, A + 16u * (uint32_t)cq, cq == 3);   // layer-3 input: [0,60) act | 60 bias | 0
+    geo_signal(cx, lane);
+    vs_mma<NK, 3>(cx, VS_X + 64 * v);
+    vs_wait(cx);   // X_v complete (and the A columns may be rewritten)
+  }
+  // ---- view pooling, thread-local: weighted mean || variance of this thread's 16 of the 64 feature columns; the density tail's
+  //      inputs are kept to two fp16 terms (hi | lo)
+  {
+    uint32_t x0[16], x1[16], x2[16];
+    tc::tmem_ld16(A + (uint32_t)VS_X + 16u * (uint32_t)cq, x0);
+    tc::tmem_ld16(A + (uint32_t)VS_X + 64u + 16u * (uint32_t)cq, x1);
+    tc::tmem_ld16(A + (uint32_t)VS_X + 128u + 16u * (uint32_t)cq, x2);
+    tc::wait_ld();
+    uint32_t mh[8], vh[8], ml[8], vl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float m[2], va[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float a0 = u2f(x0[2 * i + k]), a1 = u2f(x1[2 * i + k]), a2 = u2f(x2[2 * i + k]);
+        const float mu = pw[0] * a0 + pw[1] * a1 + pw[2] * a2;
+        const float d0 = a0 - mu, d1 = a1 - mu, d2 = a2 - mu;
+        m[k] = mu;
+        va[k] = pw[0] * d0 * d0 + pw[1] * d1 * d1 + pw[2] * d2 * d2;
+      }
+      split_h2(m[0], m[1], mh[i], ml[i]);
+      split_h2(va[0], va[1], vh[i], vl[i]);
+    }
+    const uint32_t col = A + 8u * (uint32_t)cq;
+    tc::tmem_st8(col, mh);
+    tc::tmem_st8(col + 32, vh);
+    tc::tmem_st8(col + 64, ml);
+    tc::tmem_st8(col + 96, vl);
+    if (cq == 0) {
+      const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tc::tmem_st8(A + 128, b);
+    }
+  }
+  geo_signal(cx, lane);
+  vs_mma<NK, 4>(cx, VS_D);
+  vs_wait(cx);
+  // ---- P0 (softplus, two fp16 terms out) | compress (linear; threads 0-2 keep 8 of the 24 latent values each)
+  uint32_t latq[4] = {0u, 0u, 0u, 0u};
+  {
+    uint32_t r[16];
+    tc::tmem_ld16(D + 16u * (uint32_t)cq, r);
+    if (cq < 3) {
+      uint32_t rc[8];
+      tc::tmem_ld8(D + 64u + 8u * (uint32_t)cq, rc);
+      tc::wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) latq[i] = tc::pack_h2(u2f(rc[2 * i]), u2f(rc[2 * i + 1]));
+    } else {
+      tc::wait_ld();
+    }
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_h2(sp_fast(u2f(r[2 * i])), sp_fast(u2f(r[2 * i + 1])), hi[i], lo[i]);
+    tc::tmem_st8(A + 8u * (uint32_t)cq, hi);
+    tc::tmem_st8(A + 32u + 8u * (uint32_t)cq, lo);
+    if (cq == 0) {
+      const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tc::tmem_st8(A + 64, b);
+    }
+  }
+  geo_signal(cx, lane);
+  vs_mma<NK, 5>(cx, VS_D);
+  vs_wait(cx);
+  // ---- P1 (softplus) then the 64->2 density head in fp32: a partial dot over this thread's 16 columns; the four quarters meet
+  //      through 8 words each of the row's tensor-memory lane
+  float g0 = 0.0f, rad = 0.0f;
+  {
+    uint32_t r[16];
+    tc::tmem_ld16(D + 16u * (uint32_t)cq, r);
+    tc::wait_ld();
+    const float* w0 = wp2 + 16 * cq;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float hh = sp_fast(u2f(r[i]));
+      g0 = fmaf(w0[i], hh, g0);
+      rad = fmaf(w0[64 + i], hh, rad);
+    }
+    const uint32_t xw[8] = {__float_as_uint(g0), __float_as_uint(rad), 0u, 0u, 0u, 0u, 0u, 0u};
+    tc::tmem_st8(D + 96u + 8u * (uint32_t)cq, xw);
+    tc::wait_st();
+    tc::fence_before_sync();
+    tc::named_sync(1 + q4, 128);   // the four warps of this lane quarter
+    tc::fence_after_sync();
+    uint32_t xr[32];
+    tc::tmem_ld32(D + 96u, xr);
+    tc::wait_ld();
+    g0 = (u2f(xr[0]) + u2f(xr[8])) + (u2f(xr[16]) + u2f(xr[24])) + wp2[128];
+    rad = (u2f(xr[1]) + u2f(xr[9])) + (u2f(xr[17]) + u2f(xr[25])) + wp2[129];
+  }
+  // ---- outputs (as shade_geo_kernel): alpha / sdf record, latent where a colour will be needed
+  if (live) {
+    if (cq == 0) {
+      if (query_mode) {
+        float* o = so.out5 + 5ll * id;
+        o[0] = g0; o[1] = rad; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
+      } else {
+        so.ao[so.list_base + si] = make_float2(fmaxf(rad, 0.0f), g0);
+      }
+    }
+    if (cq < 3 && (query_mode != 0 || rad > 0.0f)) lat_out[3ll * si + cq] = make_uint4(latq[0], latq[1], latq[2], latq[3]);
+  }
+}
+
+template <int NK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(VS_THREADS, 1)
+shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
+                      int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
+                      int query_mode, ShadeOut so, uint4* __restrict__ lat_out) {
+  extern __shared__ __align__(1024) uint8_t wsm[];
+  __shared__ uint64_t bars[3];            // [0] weights | [1] a_ready (32 warp arrivals of the pair; leader's copy) | [2] acc_ready
+  __shared__ uint32_t tmem_base_s;
+  __shared__ SceneS scs;
+  __shared__ __align__(16) float wp2[132];
+  constexpr TcPlan plan = make_tc_plan(NK);
+  constexpr uint32_t WBYTES = plan.st[GEO_NSTAGE].off;
+  const int t = threadIdx.x, warp = __shfl_sync(FULL, t >> 5, 0), lane = t & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int count = *count_ptr;
+  const int ntiles = (count + 127) / 128;
+  stage_scene(scs, *scp, NK, t, VS_THREADS);
+  for (int i = t; i < 130; i += VS_THREADS) wp2[i] = i < 64 ? C.w_p2[0][i] : i < 128 ? C.w_p2[1][i - 64] : C.b_p2[i - 128];
+  if (warp == 0) tc::tmem_alloc2(&tmem_base_s, 512);
+  if (t == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 32);
+    tc::mbar_init(&bars[2], 1);
+    tc::fence_mbar_init();
+  }
+  __syncthreads();
+  if (t == 0) load_weights(wsm, wpair + (size_t)rank * WBYTES, WBYTES, &bars[0]);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync_all();
+  tc::fence_after_sync();
+  const uint32_t tbase = tmem_base_s;
+  {
+    const int q4 = warp & 3, cq = warp >> 2;   // TMEM lane quarter = warp id % 4
+    GeoCtx cx;
+    cx.tm = tbase + ((uint32_t)(q4 * 32) << 16);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl) : "r"(tc::smem_u32(&bars[1])), "r"(0u));
+    cx.acc_ready = &bars[2];
+    cx.ph = 0;
+    cx.issuer = (rank == 0 && warp == 0) ? 1 : 0;
+    cx.a_ready = &bars[1];
+    cx.pha = 0;
+    cx.slot_tm = tbase;
+    cx.wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu;
+    cx.lod = (WBYTES / 2u) >> 4;
+    cx.el = tc::elect_one();
+    cx.lo_mask = two_term;
+    cx.relaxed = 1;
+    cx.l1 = 0; cx.l2 = 0;
+    // pair iteration i covers tiles 2*(i*ncl + cl) and +1; a tile index past the end is a ghost tile (takes part in every barrier)
+    for (int P = cl; 2 * P < ntiles; P += ncl)
+      vs_tile<NK>(scs, wp2, src, list, count, 2 * P + (int)rank, cx, q4, cq, lane, query_mode, so, lat_out);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync_all();
+  if (warp == 0) tc::tmem_dealloc2(tbase, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // colour kernel
 // ------------------------------------------------------------------------------------------------------------------
 template <int NK>
@@ -1214,19 +1521,24 @@ size_t tc_weight_blob_bytes(int n_kpt) { return make_tc_plan(n_kpt).total_bytes;
 size_t tc_weight_lo_bytes(int n_kpt) { return make_tc_plan(n_kpt).st[TC_NLO].off; }
 bool tc_supported(int n_views, int n_kpt, int sp_level) { return n_views == 3 && (n_kpt == 18 || n_kpt == 24) && sp_level == 3; }
 
-template <int NK>
+template <int NK, bool VSEQ = false>
 static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const uint8_t* wblob, const uint8_t* wpair, int two_term,
                                   const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode,
                                   const ShadeOut& so, uint4* lat, int2* list2, int* count2, int num_sms, cudaEvent_t after_geo, cudaStream_t st) {
   constexpr TcPlan plan = make_tc_plan(NK);
   const size_t smem_geo = plan.st[GEO_NSTAGE].off + (geo_pref(NK) ? (size_t)NSLOT * GEO_FW * 128 * 4 : 0);
   const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
+  const size_t smem_vs = plan.st[GEO_NSTAGE].off;
   static std::atomic<bool> attr[64];   // function attributes are per device (zero-initialised; setting them twice is harmless)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(shade_geo_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_geo);
     if (e != cudaSuccess) return e;
+    if constexpr (VSEQ) {
+      e = cudaFuncSetAttribute(shade_geo_vseq_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vs);
+      if (e != cudaSuccess) return e;
+    }
     e = cudaFuncSetAttribute(shade_color_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr[dev].store(true, std::memory_order_release);
@@ -1239,8 +1551,15 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   // which stages get the W_lo pass (bits 0..5) and the A_lo pass (bits 6, 7 for stages 4, 5); KPN_LO_MASK overrides (experiments)
   static const int lo_env = [] { const char* e = getenv("KPN_LO_MASK"); return e ? (int)strtol(e, nullptr, 0) : -1; }();
   two_term = two_term ? (lo_env >= 0 ? lo_env : 0xFF) : 0xC0;
-  shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat,
-                                                           relaxed_arrive);
+  if constexpr (VSEQ) {
+    const long long vt = (n_max + 127) / 128;
+    long long vp = (vt + 1) / 2;
+    const int vgrid = 2 * (int)(vp < 1 ? 1 : (vp > max_clusters ? max_clusters : vp));
+    shade_geo_vseq_kernel<NK><<<vgrid, VS_THREADS, smem_vs, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat);
+  } else {
+    shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat,
+                                                             relaxed_arrive);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (after_geo) { e = cudaEventRecord(after_geo, st); if (e != cudaSuccess) return e; }
@@ -1264,6 +1583,9 @@ cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t
                             const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode,
                             const ShadeOut& so, void* lat_scratch, void* list2, int* count2, int num_sms, cudaEvent_t after_geo,
                             cudaStream_t st) {
+  if (n_kpt == -18)   // view-sequential geometry kernel (engine 3)
+    return launch_tc_impl<18, true>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, so, (uint4*)lat_scratch,
+                                    (int2*)list2, count2, num_sms, after_geo, st);
   if (n_kpt == 18)
     return launch_tc_impl<18>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, so, (uint4*)lat_scratch,
                               (int2*)list2, count2, num_sms, after_geo, st);

@@ -61,6 +61,26 @@ __host__ __device__ constexpr int tc_kbias(int stage, int n_kpt) {
   }
 }
 
+// ---- "view-sequential" geometry kernel (engine 3, 18 keypoints): a row is a SAMPLE, its three views are run through
+// stages 0-3 one after the other, FOUR threads build / post-process a row (column quarters).  Layer-0 input of one
+// (sample, view): 96 packed columns = 4 runs of 24: threads 0-2: two keypoint pairs (14 columns) + five float4 groups of feat64
+// (10 columns); thread 3: three pairs (21) + one group (2) + the bias column.
+__host__ __device__ constexpr int vs_run_cols(int n_kpt) { return n_kpt == 18 ? 24 : 0; }
+__host__ __device__ constexpr int tc_kmap_vseq(int stage, int n_kpt, int i) {
+  if (stage != 0) return i;
+  if (i < 7 * n_kpt) {
+    const int r = i / n_kpt, k = i % n_kpt, j = k / 2;
+    const int t = j < 6 ? j / 2 : 3;
+    const int col = 24 * t + (j < 6 ? (j % 2) * 7 : (j - 6) * 7) + r;
+    return 2 * col + (k & 1);
+  }
+  const int c = i - 7 * n_kpt, g = c / 4;
+  const int t = g < 15 ? g / 5 : 3, gi = g < 15 ? g % 5 : 0;
+  const int col = 24 * t + (t < 3 ? 14 : 21) + 2 * gi + (c % 4) / 2;
+  return 2 * col + (c & 1);
+}
+__host__ __device__ constexpr int tc_kbias_vseq(int stage, int n_kpt) { return stage == 0 ? 2 * 95 : tc_kbias(stage, n_kpt); }
+
 __host__ __device__ constexpr TcPlan make_tc_plan(int n_kpt) {
   TcPlan p{};
   const int Kp[TC_NSTAGE] = {tc_k0p(n_kpt), 144, 144, 128, 144, 80, 112, 64, 32, 32, 32, 48, 32};
