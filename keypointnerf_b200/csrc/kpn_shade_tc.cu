@@ -25,6 +25,7 @@
 //          10 VIS2A 32->32 R0->R1 | 11 OUT0 37->16 R1->R0     (R0/R1: the slot's two 64-column regions, in-place epilogues)
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 #include "kpn_device.cuh"
 #include "kpn_launch.h"
 #include "kpn_tc.cuh"
@@ -1158,32 +1159,37 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
 // ------------------------------------------------------------------------------------------------------------------
 // Same network, same resident two-term weights, same CTA pairs as shade_geo_kernel, other mapping of the work onto an SM:
 //   * a tile row is a SAMPLE (128 samples per CTA, 256 per pair), not a (sample, view) pair: the three views of a sample go
-//     through stages 0-3 one after the other in the same tensor-memory lane, their 64-wide outputs X_0, X_1, X_2 stay in tensor
-//     memory, and the view pooling (reference src/utils.py:722-748) is thread-local arithmetic instead of 3-lane shuffles;
-//     the pooled stages P0|compress and P1 run once per sample instead of once per (sample, view) row;
+//     through stages 0-3 one after the other in the same tensor-memory lane; the view pooling (reference
+//     src/utils.py:722-748) is thread-local: every view's 64-wide output is folded into running sums S1 = sum pw x,
+//     S2 = sum pw x^2 held in registers (mean = S1, var = S2 - S1^2 (2 - sum pw)); the pooled stages P0|compress and P1 run
+//     once per sample instead of once per (sample, view) row;
 //   * FOUR threads per row (16 row warps = 4 lane quarters x 4 column quarters): a stage's epilogue is 32 accumulator
-//     columns per thread, every warp of the CTA works on the same stage;
-//   * one tile in flight per CTA: 14 tensor stages per tile (3 x [L0 L1 L2 L3] + P0 + P1) instead of 6 per 40 samples.
-// Tensor-memory columns (512 allocated): A [0,136) as in shade_geo_kernel's table | D [160,288) | X_0 [288,352) | X_1 [352,416)
-// | X_2 [416,480) (every access naturally aligned to its width).  L3's accumulator IS X_v.  Exchange of the four column
-// quarters' partial density sums: D columns [96,128) of the row's lane (free once the P1 accumulator has been read; rewritten
-// only by the next tile's L0).
-constexpr int VS_D = 160, VS_X = 288;
-constexpr int VS_THREADS = 16 * 32;
+//     columns per thread and every row warp of the CTA works on the same stage; a 17th warp issues the MMAs;
+//   * TWO streams of stages in flight, each with its own activation / accumulator columns, interleaved in every row warp's
+//     program: stream B runs views 0 and 2 of the current tile (8 stages), stream A the pooled stages of the PREVIOUS tile and
+//     view 1 of the current one (6 stages); while the tensor core works on one stream's stage the row warps run the other's
+//     epilogue.  8 rounds per tile instead of 14 dependent stages.
+// Tensor-memory columns (512): stream A: activations [0,136), accumulator [160,288) (its columns [96,128) double as the
+// exchange area of the four column quarters' partial density sums); stream B: activations [288,384), accumulator [384,512).
+constexpr int VS_A0 = 0, VS_D0 = 160, VS_A1 = 288, VS_D1 = 384;
+constexpr int VS_ROW_WARPS = 16;
+constexpr int VS_THREADS = (VS_ROW_WARPS + 1) * 32;
 
-template <int NK, int STAGE>
-__device__ __forceinline__ void vs_mma(GeoCtx& c, uint32_t d_col) {
-  if (c.issuer) {
-    tc::mbar_wait(c.a_ready, c.pha, 0x60u + (uint32_t)STAGE);
-    c.pha ^= 1u;
-    tc::fence_after_sync();
-    geo_issue<NK, STAGE>(c.slot_tm, c.slot_tm + d_col, c.wlo0, c.lod, c.lo_mask, c.el);
-    tc::mma_commit2_el(c.acc_ready, c.el);
-  }
+struct VsCtx {
+  uint32_t tm;                 // tensor-memory base with this row's lane field
+  uint32_t a_ready_cl[2];      // cluster-mapped address of the LEADER CTA's a_ready barrier of stream 0 (A) / 1 (B)
+  uint64_t* acc_ready[2];      // this CTA's accumulator barriers
+  uint32_t ph[2];
+};
+__device__ __forceinline__ void vs_signal(const VsCtx& c, int s, int lane) {
+  tc::wait_st();
+  tc::fence_before_sync();
+  __syncwarp();
+  if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(c.a_ready_cl[s]) : "memory");
 }
-__device__ __forceinline__ void vs_wait(GeoCtx& c) {
-  tc::mbar_wait(c.acc_ready, c.ph, 0x70u);
-  c.ph ^= 1u;
+__device__ __forceinline__ void vs_wait(VsCtx& c, int s) {
+  tc::mbar_wait(c.acc_ready[s], c.ph[s], 0x70u + (uint32_t)s);
+  c.ph[s] ^= 1u;
   tc::fence_after_sync();
 }
 // epilogue of a 128-wide softplus stage, this thread's 32 accumulator columns at d -> 16 packed columns at a
@@ -1197,217 +1203,88 @@ __device__ __forceinline__ void vs_epi_sp(uint32_t d, uint32_t a, bool bias_tail
   if (bias_tail) { o[12] = H2_ONE; o[13] = 0u; o[14] = 0u; o[15] = 0u; }
   tc::tmem_st16(a, o);
 }
+struct VsSample { float p[3]; float pw[3]; int id, si; bool live; };
 
+// stage-0 input of (sample, view v): this thread's run of 24 columns (tc_kmap_vseq) at activation base `a`
 template <int NK>
-__device__ __forceinline__ void vs_tile(const SceneS& sc, const float* __restrict__ wp2, const SampleSrc& src,
-                                        const int* __restrict__ list, int count, int tile, GeoCtx& cx, int q4, int cq, int lane,
-                                        int query_mode, const ShadeOut& so, uint4* __restrict__ lat_out) {
-  static_assert(NK == 18, "the column plan below is the 18-keypoint one (4 runs of 24 columns)");
-  const uint32_t A = cx.tm;                       // lane field = this row, column 0
-  const uint32_t D = A + (uint32_t)VS_D;
-  const int si = tile * 128 + 32 * q4 + lane;     // this row's index into the work list
-  const bool live = si < count;                   // rows past the end replay the last sample and write nothing
-  const int id = list[max(min(si, count - 1), 0)];
-  float p[3], dir[3];
-  fetch_sample(src, id, p, dir);
-  // view weights (reference src/model.py:750-759; mask == 1 for shaded samples) and the projections the gathers use
-  Proj q[3];
-  float pw[3];
-  {
-    float s = 0.0f;
+__device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, int v, int cq, uint32_t a_tm) {
+  static_assert(NK == 18, "the column plan is the 18-keypoint one (4 runs of 24 columns)");
+  float c[3];
+  const float* E = sc.E[v];
+  c[0] = E[0] * sm.p[0] + E[1] * sm.p[1] + E[2] * sm.p[2] + E[3];
+  c[1] = E[4] * sm.p[0] + E[5] * sm.p[1] + E[6] * sm.p[2] + E[7];
+  c[2] = E[8] * sm.p[0] + E[9] * sm.p[1] + E[10] * sm.p[2] + E[11];
+  const Proj q = project_s(sc, v, sm.p);
+  const Taps t64 = make_taps(q.u, q.v, sc.f64.W, sc.f64.H);
+  uint32_t a[24];
+  if (cq < 3) {
 #pragma unroll
-    for (int v = 0; v < 3; ++v) { q[v] = project_s(sc, v, p); pw[v] = boundary_weight_fast(q[v]); s += pw[v]; }
-    const float inv = 1.0f / (s + 1e-6f);
+    for (int j = 0; j < 2; ++j) {
+      float e0[7], e1[7];
+      encode_fast(sc, v, 4 * cq + 2 * j, c, e0);
+      encode_fast(sc, v, 4 * cq + 2 * j + 1, c, e1);
 #pragma unroll
-    for (int v = 0; v < 3; ++v) pw[v] *= inv;
+      for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
+    }
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+      float f[4];
+      gather_f32<1>(sc.f64, v, t64, 5 * cq + g, f);
+      a[14 + 2 * g] = tc::pack_h2(f[0], f[1]);
+      a[15 + 2 * g] = tc::pack_h2(f[2], f[3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float e0[7], e1[7];
+      encode_fast(sc, v, 12 + 2 * j, c, e0);
+      encode_fast(sc, v, 13 + 2 * j, c, e1);
+#pragma unroll
+      for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
+    }
+    float f[4];
+    gather_f32<1>(sc.f64, v, t64, 15, f);
+    a[21] = tc::pack_h2(f[0], f[1]);
+    a[22] = tc::pack_h2(f[2], f[3]);
+    a[23] = H2_ONE;
   }
+  tc::tmem_st8(a_tm + 24u * (uint32_t)cq, a);
+  tc::tmem_st8(a_tm + 24u * (uint32_t)cq + 8u, a + 8);
+  tc::tmem_st8(a_tm + 24u * (uint32_t)cq + 16u, a + 16);
+}
+// [64,72) of the stage-2 input: feat8 | bias | 0 (thread 3)
+__device__ __forceinline__ void vs_feat8(const SceneS& sc, const VsSample& sm, int v, uint32_t a_tm) {
+  uint32_t b[8] = {0u, 0u, 0u, 0u, H2_ONE, 0u, 0u, 0u};
+  const Proj q = project_s(sc, v, sm.p);
+  const Taps t8 = make_taps(q.u, q.v, sc.f8.W, sc.f8.H);
+  float g8[8];
+  gather_f32<2>(sc.f8, v, t8, 0, g8);
 #pragma unroll
-  for (int v = 0; v < 3; ++v) {
-    // ---- stage 0 input of (sample, view v): this thread's run of 24 columns (tc_kmap_vseq)
-    {
-      float c[3];
-      const float* E = sc.E[v];
-      c[0] = E[0] * p[0] + E[1] * p[1] + E[2] * p[2] + E[3];
-      c[1] = E[4] * p[0] + E[5] * p[1] + E[6] * p[2] + E[7];
-      c[2] = E[8] * p[0] + E[9] * p[1] + E[10] * p[2] + E[11];
-      const Taps t64 = make_taps(q[v].u, q[v].v, sc.f64.W, sc.f64.H);
-      uint32_t a[24];
-      if (cq < 3) {
+  for (int i = 0; i < 4; ++i) b[i] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
+  tc::tmem_st8(a_tm + 64, b);
+}
+// L3 accumulator (this thread's 16 of the 64 columns at d) folded into the pooling sums with the view's weight
+__device__ __forceinline__ void vs_accumulate(uint32_t d, float pw, float (&s1)[16], float (&s2)[16]) {
+  uint32_t x[16];
+  tc::tmem_ld16(d, x);
+  tc::wait_ld();
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float e0[7], e1[7];
-          encode_fast(sc, v, 4 * cq + 2 * j, c, e0);
-          encode_fast(sc, v, 4 * cq + 2 * j + 1, c, e1);
-#pragma unroll
-          for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
-        }
-#pragma unroll
-        for (int g = 0; g < 5; ++g) {
-          float f[4];
-          gather_f32<1>(sc.f64, v, t64, 5 * cq + g, f);
-          a[14 + 2 * g] = tc::pack_h2(f[0], f[1]);
-          a[15 + 2 * g] = tc::pack_h2(f[2], f[3]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          float e0[7], e1[7];
-          encode_fast(sc, v, 12 + 2 * j, c, e0);
-          encode_fast(sc, v, 13 + 2 * j, c, e1);
-#pragma unroll
-          for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
-        }
-        float f[4];
-        gather_f32<1>(sc.f64, v, t64, 15, f);
-        a[21] = tc::pack_h2(f[0], f[1]);
-        a[22] = tc::pack_h2(f[2], f[3]);
-        a[23] = H2_ONE;
-      }
-      // the previous view's L3 (or the previous tile's P1) has completed: every thread waited for its accumulator
-      tc::tmem_st8(A + 24u * (uint32_t)cq, a);
-      tc::tmem_st8(A + 24u * (uint32_t)cq + 8u, a + 8);
-      tc::tmem_st8(A + 24u * (uint32_t)cq + 16u, a + 16);
-    }
-    geo_signal(cx, lane);
-    vs_mma<NK, 0>(cx, VS_D);
-    vs_wait(cx);
-    // ---- L0 -> L1 -> L2 -> L3 (reference src/utils.py:691-720)
-    vs_epi_sp(D + 32u * (uint32_t)cq, A + 16u * (uint32_t)cq, false);
-    if (cq == 0) {
-      const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      tc::tmem_st8(A + 64, b);
-    }
-    geo_signal(cx, lane);
-    vs_mma<NK, 1>(cx, VS_D);
-    vs_wait(cx);
-    vs_epi_sp(D + 32u * (uint32_t)cq, A + 16u * (uint32_t)cq, false);
-    if (cq == 3) {   // [64,72): feat8 | bias | 0
-      uint32_t b[8] = {0u, 0u, 0u, 0u, H2_ONE, 0u, 0u, 0u};
-      const Taps t8 = make_taps(q[v].u, q[v].v, sc.f8.W, sc.f8.H);
-      float g8[8];
-      gather_f32<2>(sc.f8, v, t8, 0, g8);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
-      tc::tmem_st8(A + 64, b);
-    }
-    geo_signal(cx, lane);
-    vs_mma<NK, 2>(cx, VS_D);
-    vs_wait(cx);
-    vs_epi_sp(D + 32u * (uint32_t)cq, A + 16u * (uint32_t)cq, cq == 3);   // layer-3 input: [0,60) act | 60 bias | 0
-    geo_signal(cx, lane);
-    vs_mma<NK, 3>(cx, VS_X + 64 * v);
-    vs_wait(cx);   // X_v complete (and the A columns may be rewritten)
-  }
-  // ---- view pooling, thread-local: weighted mean || variance of this thread's 16 of the 64 feature columns; the density tail's
-  //      inputs are kept to two fp16 terms (hi | lo)
-  {
-    uint32_t x0[16], x1[16], x2[16];
-    tc::tmem_ld16(A + (uint32_t)VS_X + 16u * (uint32_t)cq, x0);
-    tc::tmem_ld16(A + (uint32_t)VS_X + 64u + 16u * (uint32_t)cq, x1);
-    tc::tmem_ld16(A + (uint32_t)VS_X + 128u + 16u * (uint32_t)cq, x2);
-    tc::wait_ld();
-    uint32_t mh[8], vh[8], ml[8], vl[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float m[2], va[2];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float a0 = u2f(x0[2 * i + k]), a1 = u2f(x1[2 * i + k]), a2 = u2f(x2[2 * i + k]);
-        const float mu = pw[0] * a0 + pw[1] * a1 + pw[2] * a2;
-        const float d0 = a0 - mu, d1 = a1 - mu, d2 = a2 - mu;
-        m[k] = mu;
-        va[k] = pw[0] * d0 * d0 + pw[1] * d1 * d1 + pw[2] * d2 * d2;
-      }
-      split_h2(m[0], m[1], mh[i], ml[i]);
-      split_h2(va[0], va[1], vh[i], vl[i]);
-    }
-    const uint32_t col = A + 8u * (uint32_t)cq;
-    tc::tmem_st8(col, mh);
-    tc::tmem_st8(col + 32, vh);
-    tc::tmem_st8(col + 64, ml);
-    tc::tmem_st8(col + 96, vl);
-    if (cq == 0) {
-      const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      tc::tmem_st8(A + 128, b);
-    }
-  }
-  geo_signal(cx, lane);
-  vs_mma<NK, 4>(cx, VS_D);
-  vs_wait(cx);
-  // ---- P0 (softplus, two fp16 terms out) | compress (linear; threads 0-2 keep 8 of the 24 latent values each)
-  uint32_t latq[4] = {0u, 0u, 0u, 0u};
-  {
-    uint32_t r[16];
-    tc::tmem_ld16(D + 16u * (uint32_t)cq, r);
-    if (cq < 3) {
-      uint32_t rc[8];
-      tc::tmem_ld8(D + 64u + 8u * (uint32_t)cq, rc);
-      tc::wait_ld();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) latq[i] = tc::pack_h2(u2f(rc[2 * i]), u2f(rc[2 * i + 1]));
-    } else {
-      tc::wait_ld();
-    }
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split_h2(sp_fast(u2f(r[2 * i])), sp_fast(u2f(r[2 * i + 1])), hi[i], lo[i]);
-    tc::tmem_st8(A + 8u * (uint32_t)cq, hi);
-    tc::tmem_st8(A + 32u + 8u * (uint32_t)cq, lo);
-    if (cq == 0) {
-      const uint32_t b[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-      tc::tmem_st8(A + 64, b);
-    }
-  }
-  geo_signal(cx, lane);
-  vs_mma<NK, 5>(cx, VS_D);
-  vs_wait(cx);
-  // ---- P1 (softplus) then the 64->2 density head in fp32: a partial dot over this thread's 16 columns; the four quarters meet
-  //      through 8 words each of the row's tensor-memory lane
-  float g0 = 0.0f, rad = 0.0f;
-  {
-    uint32_t r[16];
-    tc::tmem_ld16(D + 16u * (uint32_t)cq, r);
-    tc::wait_ld();
-    const float* w0 = wp2 + 16 * cq;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float hh = sp_fast(u2f(r[i]));
-      g0 = fmaf(w0[i], hh, g0);
-      rad = fmaf(w0[64 + i], hh, rad);
-    }
-    const uint32_t xw[8] = {__float_as_uint(g0), __float_as_uint(rad), 0u, 0u, 0u, 0u, 0u, 0u};
-    tc::tmem_st8(D + 96u + 8u * (uint32_t)cq, xw);
-    tc::wait_st();
-    tc::fence_before_sync();
-    tc::named_sync(1 + q4, 128);   // the four warps of this lane quarter
-    tc::fence_after_sync();
-    uint32_t xr[32];
-    tc::tmem_ld32(D + 96u, xr);
-    tc::wait_ld();
-    g0 = (u2f(xr[0]) + u2f(xr[8])) + (u2f(xr[16]) + u2f(xr[24])) + wp2[128];
-    rad = (u2f(xr[1]) + u2f(xr[9])) + (u2f(xr[17]) + u2f(xr[25])) + wp2[129];
-  }
-  // ---- outputs (as shade_geo_kernel): alpha / sdf record, latent where a colour will be needed
-  if (live) {
-    if (cq == 0) {
-      if (query_mode) {
-        float* o = so.out5 + 5ll * id;
-        o[0] = g0; o[1] = rad; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
-      } else {
-        so.ao[so.list_base + si] = make_float2(fmaxf(rad, 0.0f), g0);
-      }
-    }
-    if (cq < 3 && (query_mode != 0 || rad > 0.0f)) lat_out[3ll * si + cq] = make_uint4(latq[0], latq[1], latq[2], latq[3]);
+  for (int i = 0; i < 16; ++i) {
+    const float xv = u2f(x[i]), t = pw * xv;
+    s1[i] += t;
+    s2[i] = fmaf(t, xv, s2[i]);
   }
 }
 
 template <int NK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(VS_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(VS_THREADS, 1)   // 17 warps are allocated as 20: 96 registers per thread
 shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
                       int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
                       int query_mode, ShadeOut so, uint4* __restrict__ lat_out) {
   extern __shared__ __align__(1024) uint8_t wsm[];
-  __shared__ uint64_t bars[3];            // [0] weights | [1] a_ready (32 warp arrivals of the pair; leader's copy) | [2] acc_ready
+  // barriers: [0] weights | [1], [2] a_ready of stream A, B (32 row-warp arrivals of the pair; only the leader's copies are used) |
+  //           [3], [4] acc_ready of stream A, B (one multicast commit per stage, each CTA waits on its own copy)
+  __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_base_s;
   __shared__ SceneS scs;
   __shared__ __align__(16) float wp2[132];
@@ -1418,13 +1295,18 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
   const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int count = *count_ptr;
   const int ntiles = (count + 127) / 128;
+  // pair iterations of this cluster that have a real tile; one more iteration flushes the last tile's pooled stages
+  const int npair = (ntiles + 1) / 2;
+  const int nreal = npair > cl ? (npair - cl + ncl - 1) / ncl : 0;
   stage_scene(scs, *scp, NK, t, VS_THREADS);
   for (int i = t; i < 130; i += VS_THREADS) wp2[i] = i < 64 ? C.w_p2[0][i] : i < 128 ? C.w_p2[1][i - 64] : C.b_p2[i - 128];
   if (warp == 0) tc::tmem_alloc2(&tmem_base_s, 512);
   if (t == 0) {
     tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 32);
-    tc::mbar_init(&bars[2], 1);
+    tc::mbar_init(&bars[1], 2 * VS_ROW_WARPS);
+    tc::mbar_init(&bars[2], 2 * VS_ROW_WARPS);
+    tc::mbar_init(&bars[3], 1);
+    tc::mbar_init(&bars[4], 1);
     tc::fence_mbar_init();
   }
   __syncthreads();
@@ -1434,26 +1316,208 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
   tc::cluster_sync_all();
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
-  {
-    const int q4 = warp & 3, cq = warp >> 2;   // TMEM lane quarter = warp id % 4
-    GeoCtx cx;
+  if (warp == VS_ROW_WARPS) {
+    // ---- MMA issuer (leader CTA): the stages in the order the row warps signal them, two streams interleaved
+    if (rank == 0 && nreal > 0) {
+      const uint32_t wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu, lod = (WBYTES / 2u) >> 4, el = tc::elect_one();
+      const uint32_t a_tm[2] = {tbase + (uint32_t)VS_A0, tbase + (uint32_t)VS_A1}, d_tm[2] = {tbase + (uint32_t)VS_D0, tbase + (uint32_t)VS_D1};
+      uint32_t pha[2] = {0u, 0u};
+      auto go = [&](auto stage_c, int s) {
+        constexpr int STAGE = decltype(stage_c)::value;
+        tc::mbar_wait(&bars[1 + s], pha[s], 0x60u + 8u * (uint32_t)s + (uint32_t)STAGE);
+        pha[s] ^= 1u;
+        tc::fence_after_sync();
+        geo_issue<NK, STAGE>(a_tm[s], d_tm[s], wlo0, lod, two_term, el);
+        tc::mma_commit2_el(&bars[3 + s], el);
+      };
+      using std::integral_constant;
+      for (int it = 0; it <= nreal; ++it) {
+        go(integral_constant<int, 0>{}, 1); go(integral_constant<int, 4>{}, 0);
+        go(integral_constant<int, 1>{}, 1); go(integral_constant<int, 5>{}, 0);
+        go(integral_constant<int, 2>{}, 1); go(integral_constant<int, 0>{}, 0);
+        go(integral_constant<int, 3>{}, 1); go(integral_constant<int, 1>{}, 0);
+        go(integral_constant<int, 0>{}, 1); go(integral_constant<int, 2>{}, 0);
+        go(integral_constant<int, 1>{}, 1); go(integral_constant<int, 3>{}, 0);
+        go(integral_constant<int, 2>{}, 1);
+        go(integral_constant<int, 3>{}, 1);
+      }
+    }
+  } else if (nreal > 0) {
+    const int q4 = warp & 3, cq = warp >> 2;   // TMEM lane quarter = warp id % 4; column quarter
+    VsCtx cx;
     cx.tm = tbase + ((uint32_t)(q4 * 32) << 16);
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl) : "r"(tc::smem_u32(&bars[1])), "r"(0u));
-    cx.acc_ready = &bars[2];
-    cx.ph = 0;
-    cx.issuer = (rank == 0 && warp == 0) ? 1 : 0;
-    cx.a_ready = &bars[1];
-    cx.pha = 0;
-    cx.slot_tm = tbase;
-    cx.wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu;
-    cx.lod = (WBYTES / 2u) >> 4;
-    cx.el = tc::elect_one();
-    cx.lo_mask = two_term;
-    cx.relaxed = 1;
-    cx.l1 = 0; cx.l2 = 0;
-    // pair iteration i covers tiles 2*(i*ncl + cl) and +1; a tile index past the end is a ghost tile (takes part in every barrier)
-    for (int P = cl; 2 * P < ntiles; P += ncl)
-      vs_tile<NK>(scs, wp2, src, list, count, 2 * P + (int)rank, cx, q4, cq, lane, query_mode, so, lat_out);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl[0]) : "r"(tc::smem_u32(&bars[1])), "r"(0u));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(cx.a_ready_cl[1]) : "r"(tc::smem_u32(&bars[2])), "r"(0u));
+    cx.acc_ready[0] = &bars[3]; cx.acc_ready[1] = &bars[4];
+    cx.ph[0] = 0; cx.ph[1] = 0;
+    const uint32_t A0 = cx.tm + (uint32_t)VS_A0, D0 = cx.tm + (uint32_t)VS_D0, A1 = cx.tm + (uint32_t)VS_A1, D1 = cx.tm + (uint32_t)VS_D1;
+    const uint32_t c16 = 16u * (uint32_t)cq, c32 = 32u * (uint32_t)cq, c8 = 8u * (uint32_t)cq;
+    const uint32_t bias8[8] = {H2_ONE, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    float s1[16], s2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
+    VsSample cur;
+    cur.live = false; cur.id = 0; cur.si = 0; cur.pw[0] = cur.pw[1] = cur.pw[2] = 0.0f; cur.p[0] = cur.p[1] = cur.p[2] = 0.0f;
+    int prev_id = 0, prev_si = 0;
+    bool prev_live = false;
+    float prev_pw2 = 0.0f, prev_s0 = 0.0f;
+    for (int it = 0; it <= nreal; ++it) {
+      const int tile = 2 * (cl + it * ncl) + (int)rank;   // a tile index past the end is a ghost: every barrier, no output
+      // ================= round 0
+      // B: view 2 of the previous tile -> pooling sums; then view 0 of this tile
+      if (it > 0) {
+        vs_wait(cx, 1);
+        vs_accumulate(D1 + c16, prev_pw2, s1, s2);
+      }
+      {
+        cur.si = tile * 128 + 32 * q4 + lane;
+        cur.live = cur.si < count;
+        cur.id = list[max(min(cur.si, count - 1), 0)];
+        float dir[3];
+        fetch_sample(src, cur.id, cur.p, dir);
+        float sum = 0.0f;   // view weights (reference src/model.py:750-759; mask == 1 for shaded samples)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) { const Proj q = project_s(scs, v, cur.p); cur.pw[v] = boundary_weight_fast(q); sum += cur.pw[v]; }
+        const float inv = 1.0f / (sum + 1e-6f);
+#pragma unroll
+        for (int v = 0; v < 3; ++v) cur.pw[v] *= inv;
+      }
+      vs_build<NK>(scs, cur, 0, cq, A1);
+      vs_signal(cx, 1, lane);
+      // A: pooling of the previous tile: mean = S1, var = S2 - S1^2 (2 - sum pw) (== sum pw (x - mean)^2), two fp16 terms each
+      {
+        uint32_t mh[8], vh[8], ml[8], vl[8];
+        const float k = 2.0f - prev_s0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float m0 = s1[2 * i], m1 = s1[2 * i + 1];
+          const float v0 = fmaf(-k * m0, m0, s2[2 * i]), v1 = fmaf(-k * m1, m1, s2[2 * i + 1]);
+          split_h2(m0, m1, mh[i], ml[i]);
+          split_h2(v0, v1, vh[i], vl[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { s1[i] = 0.0f; s2[i] = 0.0f; }
+        tc::tmem_st8(A0 + c8, mh);
+        tc::tmem_st8(A0 + 32u + c8, vh);
+        tc::tmem_st8(A0 + 64u + c8, ml);
+        tc::tmem_st8(A0 + 96u + c8, vl);
+        if (cq == 0) tc::tmem_st8(A0 + 128, bias8);
+      }
+      vs_signal(cx, 0, lane);
+      // ================= round 1
+      vs_wait(cx, 1);
+      vs_epi_sp(D1 + c32, A1 + c16, false);
+      if (cq == 0) tc::tmem_st8(A1 + 64, bias8);
+      vs_signal(cx, 1, lane);
+      // A: P0 (softplus, two fp16 terms out) | compress (linear; threads 0-2 keep 8 of the 24 latent values each)
+      uint32_t latq[4] = {0u, 0u, 0u, 0u};
+      vs_wait(cx, 0);
+      {
+        uint32_t r[16];
+        tc::tmem_ld16(D0 + c16, r);
+        if (cq < 3) {
+          uint32_t rc[8];
+          tc::tmem_ld8(D0 + 64u + c8, rc);
+          tc::wait_ld();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) latq[i] = tc::pack_h2(u2f(rc[2 * i]), u2f(rc[2 * i + 1]));
+        } else {
+          tc::wait_ld();
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_h2(sp_fast(u2f(r[2 * i])), sp_fast(u2f(r[2 * i + 1])), hi[i], lo[i]);
+        tc::tmem_st8(A0 + c8, hi);
+        tc::tmem_st8(A0 + 32u + c8, lo);
+        if (cq == 0) tc::tmem_st8(A0 + 64, bias8);
+      }
+      vs_signal(cx, 0, lane);
+      // ================= round 2
+      vs_wait(cx, 1);
+      vs_epi_sp(D1 + c32, A1 + c16, false);
+      if (cq == 3) vs_feat8(scs, cur, 0, A1);
+      vs_signal(cx, 1, lane);
+      // A: P1 (softplus) + the 64->2 density head in fp32 (partial dot over this thread's 16 columns; the four quarters meet
+      //    through 8 words each of the row's tensor-memory lane) + the previous tile's outputs; then view 1 of this tile
+      vs_wait(cx, 0);
+      {
+        float g0 = 0.0f, rad = 0.0f;
+        uint32_t r[16];
+        tc::tmem_ld16(D0 + c16, r);
+        tc::wait_ld();
+        const float* w0 = wp2 + 16 * cq;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float hh = sp_fast(u2f(r[i]));
+          g0 = fmaf(w0[i], hh, g0);
+          rad = fmaf(w0[64 + i], hh, rad);
+        }
+        const uint32_t xw[8] = {__float_as_uint(g0), __float_as_uint(rad), 0u, 0u, 0u, 0u, 0u, 0u};
+        tc::tmem_st8(D0 + 96u + c8, xw);
+        tc::wait_st();
+        tc::fence_before_sync();
+        tc::named_sync(1 + q4, 128);   // the four row warps of this lane quarter
+        tc::fence_after_sync();
+        uint32_t xr[32];
+        tc::tmem_ld32(D0 + 96u, xr);
+        tc::wait_ld();
+        g0 = (u2f(xr[0]) + u2f(xr[8])) + (u2f(xr[16]) + u2f(xr[24])) + wp2[128];
+        rad = (u2f(xr[1]) + u2f(xr[9])) + (u2f(xr[17]) + u2f(xr[25])) + wp2[129];
+        // outputs (as shade_geo_kernel): alpha / sdf record, latent where a colour will be needed
+        if (prev_live) {
+          if (cq == 0) {
+            if (query_mode) {
+              float* o = so.out5 + 5ll * prev_id;
+              o[0] = g0; o[1] = rad; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
+            } else {
+              so.ao[so.list_base + prev_si] = make_float2(fmaxf(rad, 0.0f), g0);
+            }
+          }
+          if (cq < 3 && (query_mode != 0 || rad > 0.0f)) lat_out[3ll * prev_si + cq] = make_uint4(latq[0], latq[1], latq[2], latq[3]);
+        }
+      }
+      vs_build<NK>(scs, cur, 1, cq, A0);
+      vs_signal(cx, 0, lane);
+      // ================= round 3
+      vs_wait(cx, 1);
+      vs_epi_sp(D1 + c32, A1 + c16, cq == 3);   // layer-3 input: [0,60) act | 60 bias | 0
+      vs_signal(cx, 1, lane);
+      vs_wait(cx, 0);
+      vs_epi_sp(D0 + c32, A0 + c16, false);
+      if (cq == 0) tc::tmem_st8(A0 + 64, bias8);
+      vs_signal(cx, 0, lane);
+      // ================= round 4
+      vs_wait(cx, 1);
+      vs_accumulate(D1 + c16, cur.pw[0], s1, s2);
+      vs_build<NK>(scs, cur, 2, cq, A1);
+      vs_signal(cx, 1, lane);
+      vs_wait(cx, 0);
+      vs_epi_sp(D0 + c32, A0 + c16, false);
+      if (cq == 3) vs_feat8(scs, cur, 1, A0);
+      vs_signal(cx, 0, lane);
+      // ================= round 5
+      vs_wait(cx, 1);
+      vs_epi_sp(D1 + c32, A1 + c16, false);
+      if (cq == 0) tc::tmem_st8(A1 + 64, bias8);
+      vs_signal(cx, 1, lane);
+      vs_wait(cx, 0);
+      vs_epi_sp(D0 + c32, A0 + c16, cq == 3);
+      vs_signal(cx, 0, lane);
+      // ================= round 6
+      vs_wait(cx, 1);
+      vs_epi_sp(D1 + c32, A1 + c16, false);
+      if (cq == 3) vs_feat8(scs, cur, 2, A1);
+      vs_signal(cx, 1, lane);
+      vs_wait(cx, 0);
+      vs_accumulate(D0 + c16, cur.pw[1], s1, s2);
+      // ================= round 7
+      vs_wait(cx, 1);
+      vs_epi_sp(D1 + c32, A1 + c16, cq == 3);
+      vs_signal(cx, 1, lane);
+      prev_id = cur.id; prev_si = cur.si; prev_live = cur.live; prev_pw2 = cur.pw[2];
+      prev_s0 = (cur.pw[0] + cur.pw[1]) + cur.pw[2];
+    }
+    vs_wait(cx, 1);   // the last (ghost) view-2 stage: tensor memory must be idle before it is released
   }
   tc::fence_before_sync();
   __syncthreads();
