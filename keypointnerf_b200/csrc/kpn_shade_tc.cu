@@ -1173,7 +1173,14 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
 // exchange area of the four column quarters' partial density sums); stream B: activations [288,384), accumulator [384,512).
 constexpr int VS_A0 = 0, VS_D0 = 160, VS_A1 = 288, VS_D1 = 384;
 constexpr int VS_ROW_WARPS = 16;
-constexpr int VS_THREADS = (VS_ROW_WARPS + 1) * 32;
+constexpr int VS_PROD_WARPS = 7;                              // gather producers (24 warps x 80 registers)
+constexpr int VS_ITEMS = 2;                                   // (row, third) items per producer thread and pass: 7 x 32 x 2 >= 384
+constexpr int VS_THREADS = (VS_ROW_WARPS + 1 + VS_PROD_WARPS) * 32;
+// Gather staging: the producer warps blend the bilinear taps of every (row, view) pass into shared memory as packed fp16 pairs
+// (32 feat64 words + 4 feat8 words per row; word w of row r at [w * 128 + r]); the row warps' stage-0 / stage-2 builds only
+// copy them.  feat64 buffers are released by the build that consumes them (2 buffers), feat8 two rounds later (3 buffers).
+constexpr int VS_F64_WORDS = 32 * 128, VS_F8_WORDS = 4 * 128;
+constexpr int VS_STAGING_BYTES = (2 * VS_F64_WORDS + 3 * VS_F8_WORDS) * 4;
 
 struct VsCtx {
   uint32_t tm;                 // tensor-memory base with this row's lane field
@@ -1207,15 +1214,14 @@ struct VsSample { float p[3]; float pw[3]; int id, si; bool live; };
 
 // stage-0 input of (sample, view v): this thread's run of 24 columns (tc_kmap_vseq) at activation base `a`
 template <int NK>
-__device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, int v, int cq, uint32_t a_tm) {
+__device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, int v, int cq, uint32_t a_tm,
+                                         const uint32_t* __restrict__ fcol) {   // fcol: this row's column of the staged feat64 words
   static_assert(NK == 18, "the column plan is the 18-keypoint one (4 runs of 24 columns)");
   float c[3];
   const float* E = sc.E[v];
   c[0] = E[0] * sm.p[0] + E[1] * sm.p[1] + E[2] * sm.p[2] + E[3];
   c[1] = E[4] * sm.p[0] + E[5] * sm.p[1] + E[6] * sm.p[2] + E[7];
   c[2] = E[8] * sm.p[0] + E[9] * sm.p[1] + E[10] * sm.p[2] + E[11];
-  const Proj q = project_s(sc, v, sm.p);
-  const Taps t64 = make_taps(q.u, q.v, sc.f64.W, sc.f64.H);
   uint32_t a[24];
   if (cq < 3) {
 #pragma unroll
@@ -1227,12 +1233,7 @@ __device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, i
       for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
     }
 #pragma unroll
-    for (int g = 0; g < 5; ++g) {
-      float f[4];
-      gather_f32<1>(sc.f64, v, t64, 5 * cq + g, f);
-      a[14 + 2 * g] = tc::pack_h2(f[0], f[1]);
-      a[15 + 2 * g] = tc::pack_h2(f[2], f[3]);
-    }
+    for (int i = 0; i < 10; ++i) a[14 + i] = fcol[(10 * cq + i) * 128];   // float4 groups 5 cq .. 5 cq + 4
   } else {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -1242,10 +1243,8 @@ __device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, i
 #pragma unroll
       for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
     }
-    float f[4];
-    gather_f32<1>(sc.f64, v, t64, 15, f);
-    a[21] = tc::pack_h2(f[0], f[1]);
-    a[22] = tc::pack_h2(f[2], f[3]);
+    a[21] = fcol[30 * 128];   // float4 group 15
+    a[22] = fcol[31 * 128];
     a[23] = H2_ONE;
   }
   tc::tmem_st8(a_tm + 24u * (uint32_t)cq, a);
@@ -1253,14 +1252,10 @@ __device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, i
   tc::tmem_st8(a_tm + 24u * (uint32_t)cq + 16u, a + 16);
 }
 // [64,72) of the stage-2 input: feat8 | bias | 0 (thread 3)
-__device__ __forceinline__ void vs_feat8(const SceneS& sc, const VsSample& sm, int v, uint32_t a_tm) {
+__device__ __forceinline__ void vs_feat8(const uint32_t* __restrict__ gcol, uint32_t a_tm) {   // gcol: this row's staged feat8 words
   uint32_t b[8] = {0u, 0u, 0u, 0u, H2_ONE, 0u, 0u, 0u};
-  const Proj q = project_s(sc, v, sm.p);
-  const Taps t8 = make_taps(q.u, q.v, sc.f8.W, sc.f8.H);
-  float g8[8];
-  gather_f32<2>(sc.f8, v, t8, 0, g8);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) b[i] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) b[i] = gcol[i * 128];
   tc::tmem_st8(a_tm + 64, b);
 }
 // L3 accumulator (this thread's 16 of the 64 columns at d) folded into the pooling sums with the view's weight
@@ -1280,11 +1275,12 @@ template <int NK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(VS_THREADS, 1)   // 17 warps are allocated as 20: 96 registers per thread
 shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
                       int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
-                      int query_mode, ShadeOut so, uint4* __restrict__ lat_out) {
+                      int query_mode, ShadeOut so, uint4* __restrict__ lat_out, int fake_gather) {
   extern __shared__ __align__(1024) uint8_t wsm[];
   // barriers: [0] weights | [1], [2] a_ready of stream A, B (32 row-warp arrivals of the pair; only the leader's copies are used) |
   //           [3], [4] acc_ready of stream A, B (one multicast commit per stage, each CTA waits on its own copy)
-  __shared__ uint64_t bars[5];
+  //           [5],[6] full / [7],[8] empty of the two feat64 staging buffers | [9..11] full / [12..14] empty of the three feat8 ones
+  __shared__ uint64_t bars[15];
   __shared__ uint32_t tmem_base_s;
   __shared__ SceneS scs;
   __shared__ __align__(16) float wp2[132];
@@ -1295,6 +1291,12 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
   const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int count = *count_ptr;
   const int ntiles = (count + 127) / 128;
+  uint32_t* const stg64 = reinterpret_cast<uint32_t*>(wsm + WBYTES);          // [2][32][128]
+  uint32_t* const stg8 = stg64 + 2 * VS_F64_WORDS;                             // [3][4][128]
+  uint64_t* const fullF = &bars[5];
+  uint64_t* const emptyF = &bars[7];
+  uint64_t* const fullG = &bars[9];
+  uint64_t* const emptyG = &bars[12];
   // pair iterations of this cluster that have a real tile; one more iteration flushes the last tile's pooled stages
   const int npair = (ntiles + 1) / 2;
   const int nreal = npair > cl ? (npair - cl + ncl - 1) / ncl : 0;
@@ -1307,6 +1309,8 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
     tc::mbar_init(&bars[2], 2 * VS_ROW_WARPS);
     tc::mbar_init(&bars[3], 1);
     tc::mbar_init(&bars[4], 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&fullF[i], VS_PROD_WARPS); tc::mbar_init(&emptyF[i], VS_ROW_WARPS); }
+    for (int i = 0; i < 3; ++i) { tc::mbar_init(&fullG[i], VS_PROD_WARPS); tc::mbar_init(&emptyG[i], 4); }   // feat8: the 4 column-quarter-3 warps
     tc::fence_mbar_init();
   }
   __syncthreads();
@@ -1342,6 +1346,66 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
         go(integral_constant<int, 3>{}, 1);
       }
     }
+  } else if (warp > VS_ROW_WARPS) {
+    // ---- gather producers: per (tile, view) pass, 128 rows x 3 thirds of a row's 18 float4 groups (feat64 groups [6j, 6j+6);
+    //      the last third: feat64 [12,16) + the 2 feat8 groups) = 384 items, 4 per thread; bilinear taps blended in fp32
+    //      (reference src/utils.py:74-89), packed to fp16 pairs, staged for the row warps' builds
+    if (nreal > 0) {
+      const int pt = (warp - VS_ROW_WARPS - 1) * 32 + lane;
+      uint32_t phF[2] = {0u, 0u}, phG[3] = {0u, 0u, 0u};
+      int k = 0;
+      for (int it = 0; it <= nreal; ++it) {
+        const int tile = 2 * (cl + it * ncl) + (int)rank;
+        // positions of this thread's four items once per tile (four independent load chains), reused by the three views
+        float pj[VS_ITEMS][3];
+#pragma unroll
+        for (int j = 0; j < VS_ITEMS; ++j) {
+          const int si = tile * 128 + min((VS_ITEMS * pt + j) / 3, 127);
+          const int id = list[max(min(si, count - 1), 0)];
+          float dir[3];
+          fetch_sample(src, id, pj[j], dir);
+        }
+        for (int v = 0; v < 3; ++v, ++k) {
+          const int fb = k & 1, gb = k % 3;
+          if (k >= 2) { tc::mbar_wait(&emptyF[fb], phF[fb], 0x80u + (uint32_t)fb); phF[fb] ^= 1u; }
+          if (k >= 3) { tc::mbar_wait(&emptyG[gb], phG[gb], 0x84u + (uint32_t)gb); phG[gb] ^= 1u; }
+          uint32_t* f64b = stg64 + fb * VS_F64_WORDS;
+          uint32_t* f8b = stg8 + gb * VS_F8_WORDS;
+#pragma unroll
+          for (int j = 0; j < VS_ITEMS; ++j) {
+            if (fake_gather) break;   // (timing experiment: stages nothing)
+            const int item = VS_ITEMS * pt + j, row = item / 3, third = item - 3 * row;
+            if (item >= 384) break;
+            const Proj q = project_s(scs, v, pj[j]);
+            const Taps t64 = make_taps(q.u, q.v, scs.f64.W, scs.f64.H);
+            const int g0 = 6 * third;
+            {   // three float4 groups (12 tap loads in flight), then the other three: feat64, or feat64 group 15 + the feat8 pair
+              float f[12];
+              gather_f32<3>(scs.f64, v, t64, g0, f);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) f64b[(2 * g0 + i) * 128 + row] = tc::pack_h2(f[2 * i], f[2 * i + 1]);
+            }
+            if (third < 2) {
+              float f[12];
+              gather_f32<3>(scs.f64, v, t64, g0 + 3, f);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) f64b[(2 * (g0 + 3) + i) * 128 + row] = tc::pack_h2(f[2 * i], f[2 * i + 1]);
+            } else {
+              float f[4], g8[8];
+              const Taps t8 = make_taps(q.u, q.v, scs.f8.W, scs.f8.H);
+              gather_f32<1>(scs.f64, v, t64, 15, f);
+              gather_f32<2>(scs.f8, v, t8, 0, g8);
+              f64b[30 * 128 + row] = tc::pack_h2(f[0], f[1]);
+              f64b[31 * 128 + row] = tc::pack_h2(f[2], f[3]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) f8b[i * 128 + row] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) { tc::mbar_arrive(&fullF[fb]); tc::mbar_arrive(&fullG[gb]); }   // release: the warp's staged words are visible
+        }
+      }
+    }
   } else if (nreal > 0) {
     const int q4 = warp & 3, cq = warp >> 2;   // TMEM lane quarter = warp id % 4; column quarter
     VsCtx cx;
@@ -1361,8 +1425,30 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
     int prev_id = 0, prev_si = 0;
     bool prev_live = false;
     float prev_pw2 = 0.0f, prev_s0 = 0.0f;
+    uint32_t fphF[2] = {0u, 0u}, fphG[3] = {0u, 0u, 0u};   // parities of the staging buffers' "full" barriers
+    const int row = 32 * q4 + lane;
+    // the staged feat64 words of pass k (view k % 3 of iteration k / 3): wait until the producers have filled the buffer
+    auto feat64_of = [&](int k) -> const uint32_t* {
+      const int fb = k & 1;
+      tc::mbar_wait(&fullF[fb], fphF[fb], 0x90u + (uint32_t)fb);
+      fphF[fb] ^= 1u;
+      return stg64 + fb * VS_F64_WORDS + row;
+    };
+    auto feat64_done = [&](int k) {   // after the build has copied them: hand the buffer back
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&emptyF[k & 1]);
+    };
+    auto feat8_stage = [&](int k, uint32_t a_tm) {   // column-quarter-3 warps only
+      const int gb = k % 3;
+      tc::mbar_wait(&fullG[gb], fphG[gb], 0x94u + (uint32_t)gb);
+      fphG[gb] ^= 1u;
+      vs_feat8(stg8 + gb * VS_F8_WORDS + row, a_tm);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&emptyG[gb]);
+    };
     for (int it = 0; it <= nreal; ++it) {
       const int tile = 2 * (cl + it * ncl) + (int)rank;   // a tile index past the end is a ghost: every barrier, no output
+      const int k0 = 3 * it;
       // ================= round 0
       // B: view 2 of the previous tile -> pooling sums; then view 0 of this tile
       if (it > 0) {
@@ -1382,7 +1468,8 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
 #pragma unroll
         for (int v = 0; v < 3; ++v) cur.pw[v] *= inv;
       }
-      vs_build<NK>(scs, cur, 0, cq, A1);
+      vs_build<NK>(scs, cur, 0, cq, A1, feat64_of(k0));
+      feat64_done(k0);
       vs_signal(cx, 1, lane);
       // A: pooling of the previous tile: mean = S1, var = S2 - S1^2 (2 - sum pw) (== sum pw (x - mean)^2), two fp16 terms each
       {
@@ -1435,7 +1522,7 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       // ================= round 2
       vs_wait(cx, 1);
       vs_epi_sp(D1 + c32, A1 + c16, false);
-      if (cq == 3) vs_feat8(scs, cur, 0, A1);
+      if (cq == 3) feat8_stage(k0, A1);
       vs_signal(cx, 1, lane);
       // A: P1 (softplus) + the 64->2 density head in fp32 (partial dot over this thread's 16 columns; the four quarters meet
       //    through 8 words each of the row's tensor-memory lane) + the previous tile's outputs; then view 1 of this tile
@@ -1476,7 +1563,8 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
           if (cq < 3 && (query_mode != 0 || rad > 0.0f)) lat_out[3ll * prev_si + cq] = make_uint4(latq[0], latq[1], latq[2], latq[3]);
         }
       }
-      vs_build<NK>(scs, cur, 1, cq, A0);
+      vs_build<NK>(scs, cur, 1, cq, A0, feat64_of(k0 + 1));
+      feat64_done(k0 + 1);
       vs_signal(cx, 0, lane);
       // ================= round 3
       vs_wait(cx, 1);
@@ -1489,11 +1577,12 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       // ================= round 4
       vs_wait(cx, 1);
       vs_accumulate(D1 + c16, cur.pw[0], s1, s2);
-      vs_build<NK>(scs, cur, 2, cq, A1);
+      vs_build<NK>(scs, cur, 2, cq, A1, feat64_of(k0 + 2));
+      feat64_done(k0 + 2);
       vs_signal(cx, 1, lane);
       vs_wait(cx, 0);
       vs_epi_sp(D0 + c32, A0 + c16, false);
-      if (cq == 3) vs_feat8(scs, cur, 1, A0);
+      if (cq == 3) feat8_stage(k0 + 1, A0);
       vs_signal(cx, 0, lane);
       // ================= round 5
       vs_wait(cx, 1);
@@ -1506,7 +1595,7 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       // ================= round 6
       vs_wait(cx, 1);
       vs_epi_sp(D1 + c32, A1 + c16, false);
-      if (cq == 3) vs_feat8(scs, cur, 2, A1);
+      if (cq == 3) feat8_stage(k0 + 2, A1);
       vs_signal(cx, 1, lane);
       vs_wait(cx, 0);
       vs_accumulate(D0 + c16, cur.pw[1], s1, s2);
@@ -1592,7 +1681,7 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
   constexpr TcPlan plan = make_tc_plan(NK);
   const size_t smem_geo = plan.st[GEO_NSTAGE].off + (geo_pref(NK) ? (size_t)NSLOT * GEO_FW * 128 * 4 : 0);
   const size_t smem_col = plan.total_bytes - plan.st[GEO_NSTAGE].off;
-  const size_t smem_vs = plan.st[GEO_NSTAGE].off;
+  const size_t smem_vs = plan.st[GEO_NSTAGE].off + VS_STAGING_BYTES;
   static std::atomic<bool> attr[64];   // function attributes are per device (zero-initialised; setting them twice is harmless)
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1619,7 +1708,8 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
     const long long vt = (n_max + 127) / 128;
     long long vp = (vt + 1) / 2;
     const int vgrid = 2 * (int)(vp < 1 ? 1 : (vp > max_clusters ? max_clusters : vp));
-    shade_geo_vseq_kernel<NK><<<vgrid, VS_THREADS, smem_vs, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat);
+    static const int fake = [] { const char* e = getenv("KPN_VS_FAKE"); return e && e[0] == '1' ? 1 : 0; }();
+    shade_geo_vseq_kernel<NK><<<vgrid, VS_THREADS, smem_vs, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat, fake);
   } else {
     shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat,
                                                              relaxed_arrive);
