@@ -1180,7 +1180,8 @@ constexpr int VS_THREADS = (VS_ROW_WARPS + 1 + VS_PROD_WARPS) * 32;
 // (32 feat64 words + 4 feat8 words per row; word w of row r at [w * 128 + r]); the row warps' stage-0 / stage-2 builds only
 // copy them.  feat64 buffers are released by the build that consumes them (2 buffers), feat8 two rounds later (3 buffers).
 constexpr int VS_F64_WORDS = 32 * 128, VS_F8_WORDS = 4 * 128;
-constexpr int VS_STAGING_BYTES = (2 * VS_F64_WORDS + 3 * VS_F8_WORDS) * 4;
+constexpr int VS_SMP_WORDS = 4 * 128;   // per tile and row: position (3), sample id; two tiles in flight
+constexpr int VS_STAGING_BYTES = (2 * VS_F64_WORDS + 3 * VS_F8_WORDS + 2 * VS_SMP_WORDS) * 4;
 
 struct VsCtx {
   uint32_t tm;                 // tensor-memory base with this row's lane field
@@ -1280,7 +1281,8 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
   // barriers: [0] weights | [1], [2] a_ready of stream A, B (32 row-warp arrivals of the pair; only the leader's copies are used) |
   //           [3], [4] acc_ready of stream A, B (one multicast commit per stage, each CTA waits on its own copy)
   //           [5],[6] full / [7],[8] empty of the two feat64 staging buffers | [9..11] full / [12..14] empty of the three feat8 ones
-  __shared__ uint64_t bars[15];
+  //           | [15],[16] full / [17],[18] empty of the two per-tile sample buffers
+  __shared__ uint64_t bars[19];
   __shared__ uint32_t tmem_base_s;
   __shared__ SceneS scs;
   __shared__ __align__(16) float wp2[132];
@@ -1297,6 +1299,9 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
   uint64_t* const emptyF = &bars[7];
   uint64_t* const fullG = &bars[9];
   uint64_t* const emptyG = &bars[12];
+  uint32_t* const stgS = stg8 + 3 * VS_F8_WORDS;                               // [2][8][128]
+  uint64_t* const fullS = &bars[15];
+  uint64_t* const emptyS = &bars[17];
   // pair iterations of this cluster that have a real tile; one more iteration flushes the last tile's pooled stages
   const int npair = (ntiles + 1) / 2;
   const int nreal = npair > cl ? (npair - cl + ncl - 1) / ncl : 0;
@@ -1311,6 +1316,7 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
     tc::mbar_init(&bars[4], 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&fullF[i], VS_PROD_WARPS); tc::mbar_init(&emptyF[i], VS_ROW_WARPS); }
     for (int i = 0; i < 3; ++i) { tc::mbar_init(&fullG[i], VS_PROD_WARPS); tc::mbar_init(&emptyG[i], 4); }   // feat8: the 4 column-quarter-3 warps
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&fullS[i], VS_PROD_WARPS); tc::mbar_init(&emptyS[i], VS_ROW_WARPS); }
     tc::fence_mbar_init();
   }
   __syncthreads();
@@ -1352,19 +1358,30 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
     //      (reference src/utils.py:74-89), packed to fp16 pairs, staged for the row warps' builds
     if (nreal > 0) {
       const int pt = (warp - VS_ROW_WARPS - 1) * 32 + lane;
-      uint32_t phF[2] = {0u, 0u}, phG[3] = {0u, 0u, 0u};
+      uint32_t phF[2] = {0u, 0u}, phG[3] = {0u, 0u, 0u}, phS[2] = {0u, 0u};
       int k = 0;
       for (int it = 0; it <= nreal; ++it) {
         const int tile = 2 * (cl + it * ncl) + (int)rank;
-        // positions of this thread's four items once per tile (four independent load chains), reused by the three views
+        // positions of this thread's items once per tile (independent load chains), reused by the three views; the thread that
+        // owns a row's first third also stages the row's position and sample id for the row warps
+        const int sb = it & 1;
+        if (it >= 2) { tc::mbar_wait(&emptyS[sb], phS[sb], 0x88u + (uint32_t)sb); phS[sb] ^= 1u; }
         float pj[VS_ITEMS][3];
 #pragma unroll
         for (int j = 0; j < VS_ITEMS; ++j) {
-          const int si = tile * 128 + min((VS_ITEMS * pt + j) / 3, 127);
+          const int item = VS_ITEMS * pt + j, row = min(item / 3, 127);
+          const int si = tile * 128 + row;
           const int id = list[max(min(si, count - 1), 0)];
           float dir[3];
           fetch_sample(src, id, pj[j], dir);
+          if (item < 384 && item == 3 * row) {
+            uint32_t* sp = stgS + sb * VS_SMP_WORDS + row;
+            sp[0] = __float_as_uint(pj[j][0]); sp[128] = __float_as_uint(pj[j][1]); sp[256] = __float_as_uint(pj[j][2]);
+            sp[384] = (uint32_t)id;
+          }
         }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&fullS[sb]);
         for (int v = 0; v < 3; ++v, ++k) {
           const int fb = k & 1, gb = k % 3;
           if (k >= 2) { tc::mbar_wait(&emptyF[fb], phF[fb], 0x80u + (uint32_t)fb); phF[fb] ^= 1u; }
@@ -1425,7 +1442,7 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
     int prev_id = 0, prev_si = 0;
     bool prev_live = false;
     float prev_pw2 = 0.0f, prev_s0 = 0.0f;
-    uint32_t fphF[2] = {0u, 0u}, fphG[3] = {0u, 0u, 0u};   // parities of the staging buffers' "full" barriers
+    uint32_t fphF[2] = {0u, 0u}, fphG[3] = {0u, 0u, 0u}, fphS[2] = {0u, 0u};   // parities of the staging buffers' "full" barriers
     const int row = 32 * q4 + lane;
     // the staged feat64 words of pass k (view k % 3 of iteration k / 3): wait until the producers have filled the buffer
     auto feat64_of = [&](int k) -> const uint32_t* {
@@ -1455,12 +1472,17 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
         vs_wait(cx, 1);
         vs_accumulate(D1 + c16, prev_pw2, s1, s2);
       }
-      {
-        cur.si = tile * 128 + 32 * q4 + lane;
+      {   // this tile's sample: position, view weights and id staged by the producers
+        const int sb = it & 1;
+        tc::mbar_wait(&fullS[sb], fphS[sb], 0x98u + (uint32_t)sb);
+        fphS[sb] ^= 1u;
+        const uint32_t* sp = stgS + sb * VS_SMP_WORDS + row;
+        cur.si = tile * 128 + row;
         cur.live = cur.si < count;
-        cur.id = list[max(min(cur.si, count - 1), 0)];
-        float dir[3];
-        fetch_sample(src, cur.id, cur.p, dir);
+        cur.p[0] = u2f(sp[0]); cur.p[1] = u2f(sp[128]); cur.p[2] = u2f(sp[256]);
+        cur.id = (int)sp[384];
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&emptyS[sb]);
         float sum = 0.0f;   // view weights (reference src/model.py:750-759; mask == 1 for shaded samples)
 #pragma unroll
         for (int v = 0; v < 3; ++v) { const Proj q = project_s(scs, v, cur.p); cur.pw[v] = boundary_weight_fast(q); sum += cur.pw[v]; }
