@@ -17,7 +17,7 @@ The frames are exchanged with ONE NCCL all-gather.
 `value`   : inputs resident in HBM, CUDA-event time on the launch stream, max over ranks.
 `e2e`     : the same metric through the reference-facing API (`KeypointNeRF.render_pifu_nerf`) with
             pinned HOST tensors in and host tensors out (H2D + D2H inside the timed region).
-`roofline`: the dominant kernel (shade_geo_kernel): algorithmic FLOPs of the samples it shaded / its device time, both
+`roofline`: the dominant kernel (shade_geo_vseq_kernel at 18 keypoints, shade_geo_kernel at 24): algorithmic FLOPs of the samples it shaded / its device time, both
             measured live (valid-sample counter of the launch, CUDA events around the kernel on the launch stream inside the
             timed region), against the measured dense bf16 tensor peak in MEASURED_PEAKS.json; `pair` adds the colour kernel
             (executed FLOPs: 419 200 per valid sample + 79 536 per sample with density > 0).
@@ -366,14 +366,16 @@ def main():
     ach_geo = f_geo * valid * args.steps / (geo_ms * 1e-3) / 1e12 if geo_ms > 0 else None
     ach_pair = (f_geo * valid + f_ibr * coloured) * args.steps / (shade_ms * 1e-3) / 1e12 if shade_ms > 0 else None
     t_geo, t_pair, t_src = ncu_traffic()
-    roofline = {"bound": "tensor", "kernel": "shade_geo_kernel (gather + keypoint encoding + geometry MLP + pooling + density tail)",
+    vseq = n_kpt == 18 and args.engine in (0, 3)   # the library's choice of geometry kernel (include/kpnerf_b200.h, kpn_opts.engine)
+    gk = "shade_geo_vseq_kernel" if vseq else "shade_geo_kernel"
+    roofline = {"bound": "tensor", "kernel": gk + " (gather + keypoint encoding + geometry MLP + pooling + density tail)",
                 "achieved": ach_geo, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": (ach_geo / pk["tflops"]) if ach_geo else None,
                 "traffic": t_geo, "traffic_unit": "DRAM bytes per launch (one chunk = one 512x512x128 frame), ncu --set full",
                 "traffic_source": t_src, "peak_source": pk["source"],
                 "flop_per_valid_sample": f_geo, "flop_per_coloured_sample": f_ibr,
                 "valid_samples_per_step": valid, "coloured_samples_per_step": coloured,
                 "valid_frac": valid / float(n_eval), "geo_ms_per_step": geo_ms / args.steps,
-                "pair": {"kernels": "shade_geo_kernel + shade_color_kernel", "achieved": ach_pair,
+                "pair": {"kernels": gk + " + shade_color_kernel", "achieved": ach_pair,
                          "frac": (ach_pair / pk["tflops"]) if ach_pair else None, "ms_per_step": shade_ms / args.steps,
                          "traffic": t_pair},
                 "shade_launches_per_step": st["shade_launches"] / args.steps,

@@ -118,11 +118,14 @@ typedef struct {
   int fine;               /* config["fine"] */
   float ert_eps;          /* early-ray-termination transmittance threshold; 0 = off (reference behaviour) */
   const float* z_fine_override; /* optional (R, S_c+S_f) sorted depths replacing the resampled ones (test hook; same kpn_mem as kpn_out) */
-  int engine;             /* 0 = default: tcgen05, fp16 operands with two-term (hi+lo) weights, fp32 accumulate;
+  int engine;             /* 0 = default: tcgen05, fp16 operands with two-term (hi+lo) weights, fp32 accumulate; the geometry
+                                 kernel is the view-sequential one for n_kpt == 18 and the row-per-view one for n_kpt == 24;
                              1 = fp32 CUDA-core engine (parity anchor, ~25x slower; the ONLY engine for shapes the tensor-core
                                  engine does not cover: n_views != 3, n_kpt not in {18,24}, sp_level != 3 -- such shapes
                                  fail with KPN_ERR_UNSUPPORTED unless engine = 1 is requested explicitly);
-                             2 = tcgen05 with single-term fp16 weights (faster issue, ~2x the rounding error) */
+                             2 = tcgen05 (row-per-view geometry kernel) with single-term fp16 weights (~2x the rounding error);
+                             3 = as 0 but the view-sequential geometry kernel explicitly (KPN_ERR_UNSUPPORTED if n_kpt != 18);
+                             4 = as 0 but the row-per-view geometry kernel explicitly */
 } kpn_opts;
 
 /* Outputs of batch_render_pifu_nerf (reference src/model.py:1065-1096); any pointer may be NULL. */

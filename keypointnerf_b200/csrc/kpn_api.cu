@@ -397,6 +397,7 @@ extern "C" int kpn_set_scene(kpn_ctx* c, const kpn_scene* s, void* stream) {
 static int shade_batch(kpn_ctx* c, const SampleSrc& src, const int* list, const int* counter, int* counter2, long long n,
                        int query_mode, const ShadeOut& so, int engine, cudaStream_t st) {
   const bool use_tc = engine != 1;
+  if (engine < 0 || engine > 4) KPN_FAIL(c, KPN_ERR_ARG, "kpn_opts.engine = %d (0 .. 4)", engine);
   if (use_tc && !(c->tc_weights && tc_supported(c->scene_views, c->n_kpt, c->sp_level)))
     KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "the tensor-core engine covers n_views == 3, n_kpt in {18, 24}, sp_level == 3; this scene has "
              "n_views=%d n_kpt=%d sp_level=%d: request engine = 1 (fp32 CUDA-core engine, ~25x slower) explicitly",
@@ -415,7 +416,11 @@ static int shade_batch(kpn_ctx* c, const SampleSrc& src, const int* list, const 
   if (use_tc) {
     KPN_CUDA(c, c->ws_lat.reserve((size_t)n * 48));
     KPN_CUDA(c, c->ws_list2.reserve((size_t)n * 8));
-    const bool vs = engine == 3 && vs_run_cols(c->n_kpt) > 0;   // view-sequential geometry kernel (18 keypoints); else the row-per-view one
+    // geometry kernel: the view-sequential one where it is built (18 keypoints), else the row-per-view one; 3 / 4 force either
+    const bool vs_built = vs_run_cols(c->n_kpt) > 0;
+    if (engine == 3 && !vs_built)
+      KPN_FAIL(c, KPN_ERR_UNSUPPORTED, "engine 3 (view-sequential geometry kernel) is built for n_kpt == 18; this scene has %d", c->n_kpt);
+    const bool vs = vs_built && (engine == 0 || engine == 3);
     KPN_CUDA(c, launch_shade_tc(c->d_scene, c->tcc, c->wblob.as<uint8_t>(), vs ? c->wlo_vs.as<uint8_t>() : c->wlo.as<uint8_t>(),
                                 engine == 2 ? 0 : 1, vs ? -c->n_kpt : c->n_kpt, src, list, counter, n, query_mode, so, c->ws_lat.p,
                                 c->ws_list2.p, counter2, c->num_sms, em, st));

@@ -1730,7 +1730,11 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
     const long long vt = (n_max + 127) / 128;
     long long vp = (vt + 1) / 2;
     const int vgrid = 2 * (int)(vp < 1 ? 1 : (vp > max_clusters ? max_clusters : vp));
+#ifdef KPN_STAGE_TIMING   // instrumented build only: producers skip the gathers (garbage output; measures the pipeline's floor)
     static const int fake = [] { const char* e = getenv("KPN_VS_FAKE"); return e && e[0] == '1' ? 1 : 0; }();
+#else
+    const int fake = 0;
+#endif
     shade_geo_vseq_kernel<NK><<<vgrid, VS_THREADS, smem_vs, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat, fake);
   } else {
     shade_geo_kernel<NK><<<grid, GEO_THREADS, smem_geo, st>>>(sc, C, wpair, two_term, src, list, counter, query_mode, so, lat,

@@ -137,7 +137,7 @@ class KeypointNeRF(nn.Module):
         self._w_key = None
         self._scene_key = None
         self._last_bounds = None
-        self.engine = 0
+        self.engine = 0   # kpn_opts.engine: 0 tensor cores (default), 1 fp32 CUDA cores, 2-4 variants (include/kpnerf_b200.h)
 
     # ---- feature caching (reference src/model.py:642-688) -----------------------------------------
     def attach_im_feat(self, im, return_val=False):

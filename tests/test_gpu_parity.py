@@ -3,7 +3,8 @@ against (a) golden vectors produced by the reference itself and (b) the CPU orac
 seeded inputs.
 
 Gate (BASELINE.json north_star): RGB within 1e-3 abs of the reference, PSNR delta < 0.01 dB.
-  * engine 0 (tcgen05, fp16 operands with two-term weights, fp32 accumulate) is held to exactly that on RGB, on EVERY ray;
+  * engines 0 and 4 (tcgen05, fp16 operands with two-term weights, fp32 accumulate; 0 runs the view-sequential geometry kernel at
+    18 keypoints, 4 the row-per-view one everywhere) are held to exactly that on RGB, on EVERY ray;
     accumulated alpha / per-sample compositing weights / depth are looser by the factors below (they are
     not averaged by colours in [0,1] and the density head has a x30 gain in the synthetic recipe);
   * engine 1 (fp32 CUDA cores) is held to fp32 round-off.
@@ -25,11 +26,12 @@ from tests.util import checksum, load_golden, psnr, scene_from_meta
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = [0, 1]
+ENGINES = [0, 1, 4]   # default (view-sequential geometry kernel at 18 keypoints), fp32 CUDA cores, row-per-view geometry kernel
 TOL = {
     0: dict(rgb=1e-3, alpha=3e-3, contrib=3e-3, depth=3e-2, sdf=3e-2, q99_fine=2.5e-3, psnr=70.0),
     1: dict(rgb=1e-4, alpha=1e-4, contrib=1e-4, depth=2e-3, sdf=2e-3, q99_fine=1e-3, psnr=80.0),
 }
+TOL[4] = TOL[0]
 ALL = np.ones((), dtype=bool)   # every ray
 
 
@@ -105,7 +107,7 @@ def test_query_matches_reference(case, engine):
     e_sdf = np.abs(out[v][:, 0] - g["query_out"][v][:, 0]).max()
     e_rad = np.abs(out[v][:, 1] - g["query_out"][v][:, 1]).max()   # density row carries the x30 gain
     print(f"query engine {engine}: rgb {e_rgb:.2e} sdf_raw {e_sdf:.2e} rad {e_rad:.2e}")
-    assert e_rgb <= t["rgb"] and e_sdf <= 10 * t["rgb"] and e_rad <= (5e-2 if engine == 0 else 3e-3)
+    assert e_rgb <= t["rgb"] and e_sdf <= 10 * t["rgb"] and e_rad <= (5e-2 if engine != 1 else 3e-3)
     assert np.all(out[~v] == 0.0)
 
 
