@@ -73,7 +73,7 @@ struct SceneS {
   float E[3][12];   // extrinsic rows
   float C[3][4];    // source camera centres
   float4 kc[3][KPN_MAX_KPT];   // keypoints in camera space
-  float wm1, hm1, znear, inv_zrange, sp_scale, inv2sig2;
+  float wm1, hm1, znear, inv_zrange, sp_scale, inv2sig2, inv_wm1, inv_hm1;
   MapDesc f64, f8, ftex, img;
 };
 
@@ -194,7 +194,8 @@ constexpr uint32_t H2_ONE = 0x00003C00u;   // fp16 pair (1.0, 0.0): the activati
 // [0] tile start, [1] stage-0 input built, then per stage s: [2+5s] own arrive done, [3+5s] every row warp of the pair has
 // arrived, [4+5s] MMAs issued + committed, [5+5s] accumulator complete (this warp woke up), [6+5s] epilogue done.
 constexpr int TIM_TILES = 48, TIM_WORDS = 32;
-__device__ unsigned long long kpn_tim[2 * TIM_TILES * TIM_WORDS];   // rows [0, TIM_TILES): the issuer warp (h = 0); then its h = 1 partner
+__device__ unsigned long long kpn_tim[3 * TIM_TILES * TIM_WORDS];   // rows [0, TIM_TILES): the issuer warp (h = 0); then its h = 1 partner
+                                                                     // (view-sequential kernel: row warp 0, issuer, producer warp 0)
 __device__ int kpn_tim_tile[2];   // tiles each of the two warps has recorded
 #define TIM(idx) do { if (tim_on && lane == 0) kpn_tim[tim_row * TIM_WORDS + (idx)] = clock64(); } while (0)
 #else
@@ -1050,7 +1051,7 @@ __device__ __forceinline__ void stage_scene(SceneS& scs, const DevScene& g, int 
     scs.kc[i / NK][i % NK] = make_float4(g.kc[i / NK][i % NK][0], g.kc[i / NK][i % NK][1], g.kc[i / NK][i % NK][2], 0.0f);
   if (t == 0) {
     scs.wm1 = g.wm1; scs.hm1 = g.hm1; scs.znear = g.znear; scs.inv_zrange = 1.0f / (g.zfar - g.znear);
-    scs.sp_scale = g.sp_scale; scs.inv2sig2 = g.inv2sig2;
+    scs.sp_scale = g.sp_scale; scs.inv2sig2 = g.inv2sig2; scs.inv_wm1 = 1.0f / g.wm1; scs.inv_hm1 = 1.0f / g.hm1;
     scs.f64 = g.f64; scs.f8 = g.f8; scs.ftex = g.ftex; scs.img = g.img;
   }
 }
@@ -1211,7 +1212,31 @@ __device__ __forceinline__ void vs_epi_sp(uint32_t d, uint32_t a, bool bias_tail
   if (bias_tail) { o[12] = H2_ONE; o[13] = 0u; o[14] = 0u; o[15] = 0u; }
   tc::tmem_st16(a, o);
 }
+// Image coordinates of a sample for the gathers only: project_s with reciprocals instead of IEEE divisions (a few ulp in u, v --
+// the bilinear blend is continuous in them; validity and view weights use project_s).
+__device__ __forceinline__ void vs_project_uv(const SceneS& S, int v, const float p[3], float& u, float& w) {
+  const float* P = S.P[v];
+  const float hx = P[0] * p[0] + P[1] * p[1] + P[2] * p[2] + P[3];
+  const float hy = P[4] * p[0] + P[5] * p[1] + P[6] * p[2] + P[7];
+  const float hz = P[8] * p[0] + P[9] * p[1] + P[10] * p[2] + P[11];
+  const float iz = rcpf(hz);
+  u = 2.0f * (hx * iz) * S.inv_wm1 - 1.0f;
+  w = 2.0f * (hy * iz) * S.inv_hm1 - 1.0f;
+}
 struct VsSample { float p[3]; float pw[3]; int id, si; bool live; };
+#ifdef KPN_STAGE_TIMING
+// Instrumented build: cycle stamps of row warp 0 (row 0 of kpn_tim) and of the issuer warp (row 1) of block 0, per iteration
+// (tools/stage_times.py --vseq): row warp: [0] iteration start, [2n+1] n-th accumulator wait returned (the pooling build of
+// round 0 counts as a wait), [2n+2] the signal that follows it; issuer: [2g] operands of the g-th stage complete, [2g+1] committed.
+#define VT(idx) do { if (vt_on && lane == 0) kpn_tim[(size_t)it * TIM_WORDS + (idx)] = clock64(); } while (0)
+#define VI(idx) do { if (vi_on && el) kpn_tim[(size_t)(TIM_TILES + it) * TIM_WORDS + (idx)] = clock64(); } while (0)
+// producer warp 0: [0] iteration start, [1] samples staged, per view v: [2+4v] buffers free, [3+4v] / [4+4v] item 0 / 1 staged, [5+4v] arrived
+#define VP(idx) do { if (vp_on && lane == 0) kpn_tim[(size_t)(2 * TIM_TILES + it) * TIM_WORDS + (idx)] = clock64(); } while (0)
+#else
+#define VP(idx) do { } while (0)
+#define VT(idx) do { } while (0)
+#define VI(idx) do { } while (0)
+#endif
 
 // stage-0 input of (sample, view v): this thread's run of 24 columns (tc_kmap_vseq) at activation base `a`
 template <int NK>
@@ -1332,24 +1357,34 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       const uint32_t wlo0 = (tc::smem_u32(wsm) >> 4) & 0x3FFFu, lod = (WBYTES / 2u) >> 4, el = tc::elect_one();
       const uint32_t a_tm[2] = {tbase + (uint32_t)VS_A0, tbase + (uint32_t)VS_A1}, d_tm[2] = {tbase + (uint32_t)VS_D0, tbase + (uint32_t)VS_D1};
       uint32_t pha[2] = {0u, 0u};
+      int it = 0, gi = 0;
       auto go = [&](auto stage_c, int s) {
         constexpr int STAGE = decltype(stage_c)::value;
+#ifdef KPN_STAGE_TIMING
+        const bool vi_on = blockIdx.x == 0 && it < TIM_TILES;
+#endif
         tc::mbar_wait(&bars[1 + s], pha[s], 0x60u + 8u * (uint32_t)s + (uint32_t)STAGE);
         pha[s] ^= 1u;
         tc::fence_after_sync();
+        VI(2 * gi);
         geo_issue<NK, STAGE>(a_tm[s], d_tm[s], wlo0, lod, two_term, el);
         tc::mma_commit2_el(&bars[3 + s], el);
+        VI(2 * gi + 1);
+        ++gi;
       };
       using std::integral_constant;
-      for (int it = 0; it <= nreal; ++it) {
-        go(integral_constant<int, 0>{}, 1); go(integral_constant<int, 4>{}, 0);
+      gi = 15;
+      go(integral_constant<int, 0>{}, 1);   // view 0 of the first tile
+      for (it = 0; it <= nreal; ++it) {
+        gi = 0;
+        go(integral_constant<int, 4>{}, 0);
         go(integral_constant<int, 1>{}, 1); go(integral_constant<int, 5>{}, 0);
         go(integral_constant<int, 2>{}, 1); go(integral_constant<int, 0>{}, 0);
         go(integral_constant<int, 3>{}, 1); go(integral_constant<int, 1>{}, 0);
         go(integral_constant<int, 0>{}, 1); go(integral_constant<int, 2>{}, 0);
         go(integral_constant<int, 1>{}, 1); go(integral_constant<int, 3>{}, 0);
-        go(integral_constant<int, 2>{}, 1);
-        go(integral_constant<int, 3>{}, 1);
+        go(integral_constant<int, 2>{}, 1); go(integral_constant<int, 3>{}, 0);   // view 2's last stage runs on stream A's columns
+        if (it < nreal) go(integral_constant<int, 0>{}, 1);                          // view 0 of the next tile
       }
     }
   } else if (warp > VS_ROW_WARPS) {
@@ -1360,32 +1395,67 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       const int pt = (warp - VS_ROW_WARPS - 1) * 32 + lane;
       uint32_t phF[2] = {0u, 0u}, phG[3] = {0u, 0u, 0u}, phS[2] = {0u, 0u};
       int k = 0;
+      // this thread's items of a tile: sample ids, then positions (fetch_sample's arithmetic with 32-bit indices).  Both are loaded
+      // one tile ahead -- the ids under the view-0 gathers of the tile before, the positions under its view-1 gathers -- so that no
+      // tile starts with a chain of dependent global loads
+      auto load_ids = [&](int itn, int (&ids)[VS_ITEMS]) {
+        const int tile = 2 * (cl + itn * ncl) + (int)rank;
+#pragma unroll
+        for (int j = 0; j < VS_ITEMS; ++j) {
+          const int si = tile * 128 + min((VS_ITEMS * pt + j) / 3, 127);
+          ids[j] = list[max(min(si, count - 1), 0)];
+        }
+      };
+      auto load_pos = [&](const int (&ids)[VS_ITEMS], float (&pos)[VS_ITEMS][3]) {
+#pragma unroll
+        for (int j = 0; j < VS_ITEMS; ++j) {
+          const int id = ids[j];
+          if (src.mode == 0) {
+            const int r = (int)((unsigned)id / (unsigned)src.S);
+            const float z = src.z ? src.z[id] : coarse_depth(src.ray_nf[2 * r], src.ray_nf[2 * r + 1], id - r * src.S, src.S);
+            pos[j][0] = src.o[0] + src.ray_d[3 * r + 0] * z;   // eval_pts = cam_pos + cam_rays * z  (reference src/model.py:1057)
+            pos[j][1] = src.o[1] + src.ray_d[3 * r + 1] * z;
+            pos[j][2] = src.o[2] + src.ray_d[3 * r + 2] * z;
+          } else {
+            pos[j][0] = src.pts[3ll * id + 0]; pos[j][1] = src.pts[3ll * id + 1]; pos[j][2] = src.pts[3ll * id + 2];
+          }
+        }
+      };
+      int idj[VS_ITEMS], idn[VS_ITEMS];
+      float pj[VS_ITEMS][3], pjn[VS_ITEMS][3];
+      load_ids(0, idj);
+      load_pos(idj, pj);
+#pragma unroll
+      for (int j = 0; j < VS_ITEMS; ++j) { idn[j] = idj[j]; pjn[j][0] = pj[j][0]; pjn[j][1] = pj[j][1]; pjn[j][2] = pj[j][2]; }
       for (int it = 0; it <= nreal; ++it) {
-        const int tile = 2 * (cl + it * ncl) + (int)rank;
-        // positions of this thread's items once per tile (independent load chains), reused by the three views; the thread that
-        // owns a row's first third also stages the row's position and sample id for the row warps
+#ifdef KPN_STAGE_TIMING
+        const bool vp_on = blockIdx.x == 0 && warp == VS_ROW_WARPS + 1 && it < TIM_TILES;
+#endif
+        VP(0);
+        // the thread that owns a row's first third stages the row's position and sample id for the row warps
         const int sb = it & 1;
         if (it >= 2) { tc::mbar_wait(&emptyS[sb], phS[sb], 0x88u + (uint32_t)sb); phS[sb] ^= 1u; }
-        float pj[VS_ITEMS][3];
 #pragma unroll
         for (int j = 0; j < VS_ITEMS; ++j) {
           const int item = VS_ITEMS * pt + j, row = min(item / 3, 127);
-          const int si = tile * 128 + row;
-          const int id = list[max(min(si, count - 1), 0)];
-          float dir[3];
-          fetch_sample(src, id, pj[j], dir);
           if (item < 384 && item == 3 * row) {
             uint32_t* sp = stgS + sb * VS_SMP_WORDS + row;
             sp[0] = __float_as_uint(pj[j][0]); sp[128] = __float_as_uint(pj[j][1]); sp[256] = __float_as_uint(pj[j][2]);
-            sp[384] = (uint32_t)id;
+            sp[384] = (uint32_t)idj[j];
           }
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&fullS[sb]);
+        VP(1);
         for (int v = 0; v < 3; ++v, ++k) {
           const int fb = k & 1, gb = k % 3;
           if (k >= 2) { tc::mbar_wait(&emptyF[fb], phF[fb], 0x80u + (uint32_t)fb); phF[fb] ^= 1u; }
           if (k >= 3) { tc::mbar_wait(&emptyG[gb], phG[gb], 0x84u + (uint32_t)gb); phG[gb] ^= 1u; }
+          VP(2 + 4 * v);
+          if (it < nreal) {
+            if (v == 0) load_ids(it + 1, idn);
+            if (v == 1) load_pos(idn, pjn);
+          }
           uint32_t* f64b = stg64 + fb * VS_F64_WORDS;
           uint32_t* f8b = stg8 + gb * VS_F8_WORDS;
 #pragma unroll
@@ -1393,8 +1463,9 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
             if (fake_gather) break;   // (timing experiment: stages nothing)
             const int item = VS_ITEMS * pt + j, row = item / 3, third = item - 3 * row;
             if (item >= 384) break;
-            const Proj q = project_s(scs, v, pj[j]);
-            const Taps t64 = make_taps(q.u, q.v, scs.f64.W, scs.f64.H);
+            float qu, qv;
+            vs_project_uv(scs, v, pj[j], qu, qv);
+            const Taps t64 = make_taps(qu, qv, scs.f64.W, scs.f64.H);
             const int g0 = 6 * third;
             {   // three float4 groups (12 tap loads in flight), then the other three: feat64, or feat64 group 15 + the feat8 pair
               float f[12];
@@ -1409,7 +1480,7 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
               for (int i = 0; i < 6; ++i) f64b[(2 * (g0 + 3) + i) * 128 + row] = tc::pack_h2(f[2 * i], f[2 * i + 1]);
             } else {
               float f[4], g8[8];
-              const Taps t8 = make_taps(q.u, q.v, scs.f8.W, scs.f8.H);
+              const Taps t8 = make_taps(qu, qv, scs.f8.W, scs.f8.H);
               gather_f32<1>(scs.f64, v, t64, 15, f);
               gather_f32<2>(scs.f8, v, t8, 0, g8);
               f64b[30 * 128 + row] = tc::pack_h2(f[0], f[1]);
@@ -1417,10 +1488,14 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
 #pragma unroll
               for (int i = 0; i < 4; ++i) f8b[i * 128 + row] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
             }
+            VP(3 + 4 * v + j);
           }
           __syncwarp();
           if (lane == 0) { tc::mbar_arrive(&fullF[fb]); tc::mbar_arrive(&fullG[gb]); }   // release: the warp's staged words are visible
+          VP(5 + 4 * v);
         }
+#pragma unroll
+        for (int j = 0; j < VS_ITEMS; ++j) { idj[j] = idn[j]; pj[j][0] = pjn[j][0]; pj[j][1] = pjn[j][1]; pj[j][2] = pjn[j][2]; }
       }
     }
   } else if (nreal > 0) {
@@ -1463,37 +1538,45 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&emptyG[gb]);
     };
+    // sample of this row in iteration `itn` (position and id staged by the producers; a tile index past the end is a ghost: every
+    // barrier, no output) and its view-0 input -> stream B
+    auto start_tile = [&](int itn) {
+      const int tile = 2 * (cl + itn * ncl) + (int)rank;
+      const int sb = itn & 1;
+      tc::mbar_wait(&fullS[sb], fphS[sb], 0x98u + (uint32_t)sb);
+      fphS[sb] ^= 1u;
+      const uint32_t* sp = stgS + sb * VS_SMP_WORDS + row;
+      cur.si = tile * 128 + row;
+      cur.live = cur.si < count;
+      cur.p[0] = u2f(sp[0]); cur.p[1] = u2f(sp[128]); cur.p[2] = u2f(sp[256]);
+      cur.id = (int)sp[384];
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&emptyS[sb]);
+      float sum = 0.0f;   // view weights (reference src/model.py:750-759; mask == 1 for shaded samples)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) { const Proj q = project_s(scs, v, cur.p); cur.pw[v] = boundary_weight_fast(q); sum += cur.pw[v]; }
+      const float inv = 1.0f / (sum + 1e-6f);
+#pragma unroll
+      for (int v = 0; v < 3; ++v) cur.pw[v] *= inv;
+      vs_build<NK>(scs, cur, 0, cq, A1, feat64_of(3 * itn));
+      feat64_done(3 * itn);
+      vs_signal(cx, 1, lane);
+    };
+    start_tile(0);
     for (int it = 0; it <= nreal; ++it) {
-      const int tile = 2 * (cl + it * ncl) + (int)rank;   // a tile index past the end is a ghost: every barrier, no output
+#ifdef KPN_STAGE_TIMING
+      const bool vt_on = blockIdx.x == 0 && warp == 0 && it < TIM_TILES;
+#endif
+      VT(0);
       const int k0 = 3 * it;
       // ================= round 0
-      // B: view 2 of the previous tile -> pooling sums; then view 0 of this tile
+      // A: view 2 of the previous tile (its last stage ran on stream A's columns) -> pooling sums
       if (it > 0) {
-        vs_wait(cx, 1);
-        vs_accumulate(D1 + c16, prev_pw2, s1, s2);
+        vs_wait(cx, 0);   VT(1);
+        vs_accumulate(D0 + c16, prev_pw2, s1, s2);
       }
-      {   // this tile's sample: position, view weights and id staged by the producers
-        const int sb = it & 1;
-        tc::mbar_wait(&fullS[sb], fphS[sb], 0x98u + (uint32_t)sb);
-        fphS[sb] ^= 1u;
-        const uint32_t* sp = stgS + sb * VS_SMP_WORDS + row;
-        cur.si = tile * 128 + row;
-        cur.live = cur.si < count;
-        cur.p[0] = u2f(sp[0]); cur.p[1] = u2f(sp[128]); cur.p[2] = u2f(sp[256]);
-        cur.id = (int)sp[384];
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&emptyS[sb]);
-        float sum = 0.0f;   // view weights (reference src/model.py:750-759; mask == 1 for shaded samples)
-#pragma unroll
-        for (int v = 0; v < 3; ++v) { const Proj q = project_s(scs, v, cur.p); cur.pw[v] = boundary_weight_fast(q); sum += cur.pw[v]; }
-        const float inv = 1.0f / (sum + 1e-6f);
-#pragma unroll
-        for (int v = 0; v < 3; ++v) cur.pw[v] *= inv;
-      }
-      vs_build<NK>(scs, cur, 0, cq, A1, feat64_of(k0));
-      feat64_done(k0);
-      vs_signal(cx, 1, lane);
       // A: pooling of the previous tile: mean = S1, var = S2 - S1^2 (2 - sum pw) (== sum pw (x - mean)^2), two fp16 terms each
+   
       {
         uint32_t mh[8], vh[8], ml[8], vl[8];
         const float k = 2.0f - prev_s0;
@@ -1512,15 +1595,15 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
         tc::tmem_st8(A0 + 96u + c8, vl);
         if (cq == 0) tc::tmem_st8(A0 + 128, bias8);
       }
-      vs_signal(cx, 0, lane);
+      vs_signal(cx, 0, lane);   VT(2);
       // ================= round 1
-      vs_wait(cx, 1);
+      vs_wait(cx, 1);   VT(3);
       vs_epi_sp(D1 + c32, A1 + c16, false);
       if (cq == 0) tc::tmem_st8(A1 + 64, bias8);
-      vs_signal(cx, 1, lane);
+      vs_signal(cx, 1, lane);   VT(4);
       // A: P0 (softplus, two fp16 terms out) | compress (linear; threads 0-2 keep 8 of the 24 latent values each)
       uint32_t latq[4] = {0u, 0u, 0u, 0u};
-      vs_wait(cx, 0);
+      vs_wait(cx, 0);   VT(5);
       {
         uint32_t r[16];
         tc::tmem_ld16(D0 + c16, r);
@@ -1540,15 +1623,15 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
         tc::tmem_st8(A0 + 32u + c8, lo);
         if (cq == 0) tc::tmem_st8(A0 + 64, bias8);
       }
-      vs_signal(cx, 0, lane);
+      vs_signal(cx, 0, lane);   VT(6);
       // ================= round 2
-      vs_wait(cx, 1);
+      vs_wait(cx, 1);   VT(7);
       vs_epi_sp(D1 + c32, A1 + c16, false);
       if (cq == 3) feat8_stage(k0, A1);
-      vs_signal(cx, 1, lane);
+      vs_signal(cx, 1, lane);   VT(8);
       // A: P1 (softplus) + the 64->2 density head in fp32 (partial dot over this thread's 16 columns; the four quarters meet
       //    through 8 words each of the row's tensor-memory lane) + the previous tile's outputs; then view 1 of this tile
-      vs_wait(cx, 0);
+      vs_wait(cx, 0);   VT(9);
       {
         float g0 = 0.0f, rad = 0.0f;
         uint32_t r[16];
@@ -1587,48 +1670,56 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       }
       vs_build<NK>(scs, cur, 1, cq, A0, feat64_of(k0 + 1));
       feat64_done(k0 + 1);
-      vs_signal(cx, 0, lane);
+      vs_signal(cx, 0, lane);   VT(10);
       // ================= round 3
-      vs_wait(cx, 1);
+      vs_wait(cx, 1);   VT(11);
       vs_epi_sp(D1 + c32, A1 + c16, cq == 3);   // layer-3 input: [0,60) act | 60 bias | 0
-      vs_signal(cx, 1, lane);
-      vs_wait(cx, 0);
+      vs_signal(cx, 1, lane);   VT(12);
+      vs_wait(cx, 0);   VT(13);
       vs_epi_sp(D0 + c32, A0 + c16, false);
       if (cq == 0) tc::tmem_st8(A0 + 64, bias8);
-      vs_signal(cx, 0, lane);
+      vs_signal(cx, 0, lane);   VT(14);
       // ================= round 4
-      vs_wait(cx, 1);
+      vs_wait(cx, 1);   VT(15);
       vs_accumulate(D1 + c16, cur.pw[0], s1, s2);
       vs_build<NK>(scs, cur, 2, cq, A1, feat64_of(k0 + 2));
       feat64_done(k0 + 2);
-      vs_signal(cx, 1, lane);
-      vs_wait(cx, 0);
+      vs_signal(cx, 1, lane);   VT(16);
+      vs_wait(cx, 0);   VT(17);
       vs_epi_sp(D0 + c32, A0 + c16, false);
       if (cq == 3) feat8_stage(k0 + 1, A0);
-      vs_signal(cx, 0, lane);
+      vs_signal(cx, 0, lane);   VT(18);
       // ================= round 5
-      vs_wait(cx, 1);
+      vs_wait(cx, 1);   VT(19);
       vs_epi_sp(D1 + c32, A1 + c16, false);
       if (cq == 0) tc::tmem_st8(A1 + 64, bias8);
-      vs_signal(cx, 1, lane);
-      vs_wait(cx, 0);
+      vs_signal(cx, 1, lane);   VT(20);
+      vs_wait(cx, 0);   VT(21);
       vs_epi_sp(D0 + c32, A0 + c16, cq == 3);
-      vs_signal(cx, 0, lane);
+      vs_signal(cx, 0, lane);   VT(22);
       // ================= round 6
-      vs_wait(cx, 1);
+      vs_wait(cx, 1);   VT(23);
       vs_epi_sp(D1 + c32, A1 + c16, false);
       if (cq == 3) feat8_stage(k0 + 2, A1);
-      vs_signal(cx, 1, lane);
-      vs_wait(cx, 0);
+      vs_signal(cx, 1, lane);   VT(24);
+      vs_wait(cx, 0);   VT(25);
       vs_accumulate(D0 + c16, cur.pw[1], s1, s2);
+      VT(26);
+   
       // ================= round 7
-      vs_wait(cx, 1);
-      vs_epi_sp(D1 + c32, A1 + c16, cq == 3);
-      vs_signal(cx, 1, lane);
+      // view 2's last stage moves to stream A (idle since round 6): its input goes to A's activation columns; stream B is then
+      // free for view 0 of the next tile while that stage runs
+      vs_wait(cx, 1);   VT(27);
+      vs_epi_sp(D1 + c32, A0 + c16, cq == 3);
+      vs_signal(cx, 0, lane);   VT(28);
       prev_id = cur.id; prev_si = cur.si; prev_live = cur.live; prev_pw2 = cur.pw[2];
       prev_s0 = (cur.pw[0] + cur.pw[1]) + cur.pw[2];
+      if (it < nreal) { start_tile(it + 1);   VT(29); }
     }
-    vs_wait(cx, 1);   // the last (ghost) view-2 stage: tensor memory must be idle before it is released
+#ifdef KPN_STAGE_TIMING
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) { kpn_tim_tile[0] = min(nreal + 1, TIM_TILES); kpn_tim_tile[1] = kpn_tim_tile[0]; }
+#endif
+    vs_wait(cx, 0);   // the last (ghost) view-2 stage: tensor memory must be idle before it is released
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -1802,7 +1893,7 @@ cudaError_t tc_stage_times(unsigned long long* out, int n_words, int* n_tiles) {
   e = cudaMemcpyFromSymbol(nt, kpn_tim_tile, sizeof(nt));
   if (e != cudaSuccess) return e;
   *n_tiles = nt[0] < nt[1] ? nt[0] : nt[1];
-  const size_t bytes = sizeof(unsigned long long) * (size_t)(n_words < 2 * TIM_TILES * TIM_WORDS ? n_words : 2 * TIM_TILES * TIM_WORDS);
+  const size_t bytes = sizeof(unsigned long long) * (size_t)(n_words < 3 * TIM_TILES * TIM_WORDS ? n_words : 3 * TIM_TILES * TIM_WORDS);
   e = cudaMemcpyFromSymbol(out, kpn_tim, bytes);
   if (e != cudaSuccess) return e;
   const int zero[2] = {0, 0};

@@ -54,6 +54,7 @@ def test_vseq_query_and_frame_agree_with_fp32_engine():
     m.check_health()
     flipped = (f3["alpha"] - f1["alpha"]).abs() > 0.05
     e = float((f3["tex_fg"] - f1["tex_fg"]).abs().amax(0)[~flipped].max())
-    e0 = float((f0["tex_fg"] - f1["tex_fg"]).abs().amax(0)[~flipped].max())
+    flipped0 = (f0["alpha"] - f1["alpha"]).abs() > 0.05   # (rays on the final-sample step flip independently per engine)
+    e0 = float((f0["tex_fg"] - f1["tex_fg"]).abs().amax(0)[~flipped0].max())
     print(f"vseq 256^2x96 frame vs fp32 engine: max rgb err {e:.2e} (engine 4: {e0:.2e}), flipped {float(flipped.float().mean()):.4%}")
     assert e < 1e-3 and float(flipped.float().mean()) < 0.01

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Where one tile of the geometry kernel spends its cycles: renders the bench frame with the instrumented library
-(-DKPN_STAGE_TIMING: cycle stamps of one issuer warp, block 0 / slot 0) and prints, per stage, the medians of
-  build/epilogue (CUDA cores) | own arrive -> all 16 row warps arrived | MMA issue | commit -> accumulator visible.
+"""Where the geometry kernel spends its cycles: renders the bench frame with the instrumented library (-DKPN_STAGE_TIMING:
+cycle stamps of a few warps of block 0) and prints medians per stage.
 
-    python tools/stage_times.py            # builds keypointnerf_b200/lib/libkpnerf_b200_timing.so if missing (needs nvcc)
+    python tools/stage_times.py            # view-sequential kernel (engine 0 at 18 keypoints): row warp 0, issuer, producer warp 0
+    python tools/stage_times.py --engine4  # row-per-view kernel: one issuer warp and its column-half partner
+    python tools/stage_times.py --build    # only (re)build keypointnerf_b200/lib/libkpnerf_b200_timing.so (needs nvcc)
 """
 import ctypes as C
 import os
@@ -26,25 +27,62 @@ import torch  # noqa: E402
 from keypointnerf_b200 import synthetic as syn  # noqa: E402
 from keypointnerf_b200.testing import build_model, scene_tensors  # noqa: E402
 
+ROWS, TILES, WORDS = 3, 48, 32
+engine = 4 if "--engine4" in sys.argv else 0
 n_kpt = 18
 scene, weights, target = syn.make_scene(512, 3, n_kpt), syn.make_weights(n_kpt), syn.make_target(512)
 net = build_model(weights, n_kpt, "cuda:0")
 a = scene_tensors(scene, target, "cuda:0")
 m = net._bind_scene(a["cam"], a["feat_geo"], a["feat_tex"], a["sp_data"], a["img"], a["fg"], a["bounds"])
-kw = dict(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=512, ny=512, S_c=128)
-buf = (C.c_ulonglong * (2 * 48 * 32))()
+kw = dict(K=a["cam_tar"]["K"], RT=a["cam_tar"]["RT"], znear=2.0, zfar=5.0, x0=0, y0=0, step=1, nx=512, ny=512, S_c=128, engine=engine)
+buf = (C.c_ulonglong * (ROWS * TILES * WORDS))()
 nt = C.c_int(0)
 m.lib.kpn_debug_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
 for it in range(3):
     m.render(**kw)
     torch.cuda.synchronize()
-    rc = m.lib.kpn_debug_stage_times(m.ctx, buf, 2 * 48 * 32, C.byref(nt))
+    rc = m.lib.kpn_debug_stage_times(m.ctx, buf, ROWS * TILES * WORDS, C.byref(nt))
     assert rc == 0, rc
-both = np.frombuffer(buf, dtype=np.uint64).reshape(2, 48, 32).astype(np.int64)
-t = both[0][4:nt.value]   # the issuer warp; skip the first tiles (cold)
-t1 = both[1][4:nt.value]  # its column-half-1 partner (same rows, other warp)
-print(f"tiles recorded: {nt.value}; medians in SM cycles over {len(t)} tiles of one issuer warp (slot 0 of cluster 0)")
+rec = np.frombuffer(buf, dtype=np.uint64).reshape(ROWS, TILES, WORDS).astype(np.int64)
 med = lambda x: float(np.median(x))
+
+if engine == 0:
+    # view-sequential kernel: row 0 = row warp 0, row 1 = the issuer warp, row 2 = producer warp 0; one record per iteration
+    n = nt.value
+    r, i, p = rec[0][8:n - 1], rec[1][8:n - 1], rec[2][8:n - 1]
+    rn, pn = rec[0][9:n], rec[2][9:n]      # the next iteration's records
+    # the 14 stages of an iteration in issue order: name, row-warp stamp where its CUDA-core work starts, stamp of its signal,
+    # stamp where its accumulator wait returns, stamp just before that wait is entered (>= 32: the next iteration's record)
+    T = [("A4 P0|C", 1, 2, 5, 4), ("B1 v0", 3, 4, 7, 6), ("A5 P1", 5, 6, 9, 8), ("B2 v0", 7, 8, 11, 10), ("A0 v1", 9, 10, 13, 12),
+         ("B3 v0", 11, 12, 15, 14), ("A1 v1", 13, 14, 17, 16), ("B0 v2", 15, 16, 19, 18), ("A2 v1", 17, 18, 21, 20),
+         ("B1 v2", 19, 20, 23, 22), ("A3 v1", 21, 22, 25, 24), ("B2 v2", 23, 24, 27, 26), ("A3 v2", 27, 28, 32 + 1, 32 + 0),
+         ("B0 v0'", 28, 29, 32 + 3, 32 + 2)]
+    col = lambda j: r[:, j] if j < 32 else rn[:, j - 32]
+    print(f"iterations recorded: {n}; medians in SM cycles; iteration period {med(rn[:, 0] - r[:, 0]):.0f}")
+    print(f"{'stage':8s} {'cuda work':>10s} {'sig->issuer':>12s} {'issue':>7s} {'commit->wake':>13s} {'round trip':>11s} {'waited':>7s}")
+    tot = np.zeros(6)
+    for g, (nm, start, sig, wake, before) in enumerate(T):
+        vals = [med(col(sig) - col(start)), med(i[:, 2 * g] - col(sig)), med(i[:, 2 * g + 1] - i[:, 2 * g]), med(col(wake) - i[:, 2 * g + 1]),
+                med(col(wake) - col(sig)), med(col(wake) - col(before))]
+        tot += vals
+        print(f"{nm:8s} " + " ".join(f"{v:{w}.0f}" for v, w in zip(vals, (10, 12, 7, 13, 11, 7))))
+    print(f"{'sum':8s} " + " ".join(f"{v:{w}.0f}" for v, w in zip(tot, (10, 12, 7, 13, 11, 7))))
+    print(f"view-1 accumulate (no signal): {med(r[:, 26] - r[:, 25]):.0f}")
+    # producer warp 0: [0] iteration start, [1] samples staged, per view v: [2+4v] buffers free, [3+4v] item 0 done, [4+4v] item 1
+    # done, [5+4v] arrived
+    print(f"producer warp 0: iteration period {med(pn[:, 0] - p[:, 0]):.0f}; sample buffer wait + staging {med(p[:, 1] - p[:, 0]):.0f}")
+    for v in range(3):
+        prev_end = p[:, 1] if v == 0 else p[:, 5 + 4 * (v - 1)]
+        # view 0 of iteration it is consumed by the build at the END of iteration it - 1 (stamp 29 of the previous record)
+        sig = r[:, 10] if v == 1 else r[:, 16] if v == 2 else rec[0][7:n - 2][:, 29]
+        print(f"  view {v}: waited for buffers {med(p[:, 2 + 4 * v] - prev_end):6.0f}  item 0 {med(p[:, 3 + 4 * v] - p[:, 2 + 4 * v]):6.0f}  "
+              f"item 1 {med(p[:, 4 + 4 * v] - p[:, 3 + 4 * v]):6.0f}  arrive {med(p[:, 5 + 4 * v] - p[:, 4 + 4 * v]):5.0f}   "
+              f"arrive -> row warp 0 has built and signalled: {med(sig - p[:, 5 + 4 * v]):7.0f}")
+    sys.exit(0)
+
+t = rec[0][4:nt.value]   # the issuer warp; skip the first tiles (cold)
+t1 = rec[1][4:nt.value]  # its column-half-1 partner (same rows, other warp)
+print(f"tiles recorded: {nt.value}; medians in SM cycles over {len(t)} tiles of one issuer warp (slot 0 of cluster 0)")
 tile = med(t[1:, 0] - t[:-1, 0])
 print(f"tile period (start -> next start of the same slot): {tile:.0f}")
 print(f"stage-0 input build: {med(t[:, 1] - t[:, 0]):.0f}")
