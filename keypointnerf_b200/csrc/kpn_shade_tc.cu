@@ -194,7 +194,7 @@ constexpr uint32_t H2_ONE = 0x00003C00u;   // fp16 pair (1.0, 0.0): the activati
 // [0] tile start, [1] stage-0 input built, then per stage s: [2+5s] own arrive done, [3+5s] every row warp of the pair has
 // arrived, [4+5s] MMAs issued + committed, [5+5s] accumulator complete (this warp woke up), [6+5s] epilogue done.
 constexpr int TIM_TILES = 48, TIM_WORDS = 32;
-__device__ unsigned long long kpn_tim[3 * TIM_TILES * TIM_WORDS];   // rows [0, TIM_TILES): the issuer warp (h = 0); then its h = 1 partner
+__device__ unsigned long long kpn_tim[3 * TIM_TILES * TIM_WORDS + 256];   // (+ 256: cycles every block of the view-sequential kernel took)   // rows [0, TIM_TILES): the issuer warp (h = 0); then its h = 1 partner
                                                                      // (view-sequential kernel: row warp 0, issuer, producer warp 0)
 __device__ int kpn_tim_tile[2];   // tiles each of the two warps has recorded
 #define TIM(idx) do { if (tim_on && lane == 0) kpn_tim[tim_row * TIM_WORDS + (idx)] = clock64(); } while (0)
@@ -1156,7 +1156,7 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// view-sequential geometry + density kernel (engine 3, 18 keypoints)
+// view-sequential geometry + density kernel (18 keypoints: the default geometry kernel there; engine 3 requests it explicitly)
 // ------------------------------------------------------------------------------------------------------------------
 // Same network, same resident two-term weights, same CTA pairs as shade_geo_kernel, other mapping of the work onto an SM:
 //   * a tile row is a SAMPLE (128 samples per CTA, 256 per pair), not a (sample, view) pair: the three views of a sample go
@@ -1166,22 +1166,24 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
 //     once per sample instead of once per (sample, view) row;
 //   * FOUR threads per row (16 row warps = 4 lane quarters x 4 column quarters): a stage's epilogue is 32 accumulator
 //     columns per thread and every row warp of the CTA works on the same stage; a 17th warp issues the MMAs;
-//   * TWO streams of stages in flight, each with its own activation / accumulator columns, interleaved in every row warp's
-//     program: stream B runs views 0 and 2 of the current tile (8 stages), stream A the pooled stages of the PREVIOUS tile and
-//     view 1 of the current one (6 stages); while the tensor core works on one stream's stage the row warps run the other's
-//     epilogue.  8 rounds per tile instead of 14 dependent stages.
+//   * TWO streams of 7 stages each in flight, each with its own activation / accumulator columns, interleaved in every row
+//     warp's program: stream B runs views 0 and 2 of the current tile except view 2's last stage, stream A the pooled stages of
+//     the PREVIOUS tile, view 1 of the current one and view 2's last stage (whose input the row warps write into A's columns);
+//     view 0 of the NEXT tile is built while that stage runs.  While the tensor core works on one stream's stage the row warps
+//     run the other's epilogue: 8 rounds per tile instead of 14 dependent stages;
+//   * 7 more warps only gather (below): the row warps never wait for global memory.
 // Tensor-memory columns (512): stream A: activations [0,136), accumulator [160,288) (its columns [96,128) double as the
 // exchange area of the four column quarters' partial density sums); stream B: activations [288,384), accumulator [384,512).
 constexpr int VS_A0 = 0, VS_D0 = 160, VS_A1 = 288, VS_D1 = 384;
 constexpr int VS_ROW_WARPS = 16;
 constexpr int VS_PROD_WARPS = 7;                              // gather producers (24 warps x 80 registers)
-constexpr int VS_ITEMS = 2;                                   // (row, third) items per producer thread and pass: 7 x 32 x 2 >= 384
 constexpr int VS_THREADS = (VS_ROW_WARPS + 1 + VS_PROD_WARPS) * 32;
 // Gather staging: the producer warps blend the bilinear taps of every (row, view) pass into shared memory as packed fp16 pairs
-// (32 feat64 words + 4 feat8 words per row; word w of row r at [w * 128 + r]); the row warps' stage-0 / stage-2 builds only
-// copy them.  feat64 buffers are released by the build that consumes them (2 buffers), feat8 two rounds later (3 buffers).
+// (32 feat64 words + 4 feat8 words per row; feat64 word w of row r at vs_f64_word(w, r), feat8 word w at [w * 128 + r]); the row
+// warps' stage-0 / stage-2 builds only copy them.  feat64 buffers are released by the build that consumes them (2 buffers),
+// feat8 two rounds later (3 buffers).  They also stage every tile's sample positions and ids (loaded one tile ahead).
 constexpr int VS_F64_WORDS = 32 * 128, VS_F8_WORDS = 4 * 128;
-constexpr int VS_SMP_WORDS = 4 * 128;   // per tile and row: position (3), sample id; two tiles in flight
+constexpr int VS_SMP_WORDS = 8 * 128;   // per tile and row: position (3), sample id, view weights (3), -; two tiles in flight
 constexpr int VS_STAGING_BYTES = (2 * VS_F64_WORDS + 3 * VS_F8_WORDS + 2 * VS_SMP_WORDS) * 4;
 
 struct VsCtx {
@@ -1223,14 +1225,17 @@ __device__ __forceinline__ void vs_project_uv(const SceneS& S, int v, const floa
   u = 2.0f * (hx * iz) * S.inv_wm1 - 1.0f;
   w = 2.0f * (hy * iz) * S.inv_hm1 - 1.0f;
 }
-struct VsSample { float p[3]; float pw[3]; int id, si; bool live; };
+// feat64 staging: word w (channels 2w, 2w + 1) of row r.  The producers write eight float4 groups of a row from eight adjacent
+// lanes; the XOR spreads them over the banks, and a row warp's 32 rows of one word stay on 32 banks.
+__device__ __forceinline__ int vs_f64_word(int w, int row) { return w * 128 + (row ^ (4 * ((w >> 1) & 7))); }
+struct VsSample { float p[3]; float pw[3]; int id, si, row; bool live; };
 #ifdef KPN_STAGE_TIMING
 // Instrumented build: cycle stamps of row warp 0 (row 0 of kpn_tim) and of the issuer warp (row 1) of block 0, per iteration
 // (tools/stage_times.py --vseq): row warp: [0] iteration start, [2n+1] n-th accumulator wait returned (the pooling build of
 // round 0 counts as a wait), [2n+2] the signal that follows it; issuer: [2g] operands of the g-th stage complete, [2g+1] committed.
 #define VT(idx) do { if (vt_on && lane == 0) kpn_tim[(size_t)it * TIM_WORDS + (idx)] = clock64(); } while (0)
 #define VI(idx) do { if (vi_on && el) kpn_tim[(size_t)(TIM_TILES + it) * TIM_WORDS + (idx)] = clock64(); } while (0)
-// producer warp 0: [0] iteration start, [1] samples staged, per view v: [2+4v] buffers free, [3+4v] / [4+4v] item 0 / 1 staged, [5+4v] arrived
+// producer warp 0: [0] iteration start, [1] samples staged, per view v: [2+4v] buffers free, [3+4v] last unit staged, [5+4v] arrived
 #define VP(idx) do { if (vp_on && lane == 0) kpn_tim[(size_t)(2 * TIM_TILES + it) * TIM_WORDS + (idx)] = clock64(); } while (0)
 #else
 #define VP(idx) do { } while (0)
@@ -1241,7 +1246,7 @@ struct VsSample { float p[3]; float pw[3]; int id, si; bool live; };
 // stage-0 input of (sample, view v): this thread's run of 24 columns (tc_kmap_vseq) at activation base `a`
 template <int NK>
 __device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, int v, int cq, uint32_t a_tm,
-                                         const uint32_t* __restrict__ fcol) {   // fcol: this row's column of the staged feat64 words
+                                         const uint32_t* __restrict__ fbuf) {   // fbuf: the staged feat64 words of this pass
   static_assert(NK == 18, "the column plan is the 18-keypoint one (4 runs of 24 columns)");
   float c[3];
   const float* E = sc.E[v];
@@ -1259,7 +1264,7 @@ __device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, i
       for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
     }
 #pragma unroll
-    for (int i = 0; i < 10; ++i) a[14 + i] = fcol[(10 * cq + i) * 128];   // float4 groups 5 cq .. 5 cq + 4
+    for (int i = 0; i < 10; ++i) a[14 + i] = fbuf[vs_f64_word(10 * cq + i, sm.row)];   // float4 groups 5 cq .. 5 cq + 4
   } else {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -1269,8 +1274,8 @@ __device__ __forceinline__ void vs_build(const SceneS& sc, const VsSample& sm, i
 #pragma unroll
       for (int r = 0; r < 7; ++r) a[7 * j + r] = tc::pack_h2(e0[r], e1[r]);
     }
-    a[21] = fcol[30 * 128];   // float4 group 15
-    a[22] = fcol[31 * 128];
+    a[21] = fbuf[vs_f64_word(30, sm.row)];   // float4 group 15
+    a[22] = fbuf[vs_f64_word(31, sm.row)];
     a[23] = H2_ONE;
   }
   tc::tmem_st8(a_tm + 24u * (uint32_t)cq, a);
@@ -1351,6 +1356,15 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
   tc::cluster_sync_all();
   tc::fence_after_sync();
   const uint32_t tbase = tmem_base_s;
+#ifdef KPN_STAGE_TIMING
+  const long long blk_t0 = clock64();
+  const int tim_blk = fake_gather >> 8;
+  fake_gather &= 0xff;
+#endif
+  // registers: the row warps hand 8 per thread to the issuer / producer warps, whose gathers keep 16 tap loads (64 registers) in
+  // flight per thread -- global-memory latency times loads in flight is what bounds the producers
+  if (warp < VS_ROW_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
   if (warp == VS_ROW_WARPS) {
     // ---- MMA issuer (leader CTA): the stages in the order the row warps signal them, two streams interleaved
     if (rank == 0 && nreal > 0) {
@@ -1361,7 +1375,7 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       auto go = [&](auto stage_c, int s) {
         constexpr int STAGE = decltype(stage_c)::value;
 #ifdef KPN_STAGE_TIMING
-        const bool vi_on = blockIdx.x == 0 && it < TIM_TILES;
+        const bool vi_on = (int)blockIdx.x == tim_blk && it < TIM_TILES;
 #endif
         tc::mbar_wait(&bars[1 + s], pha[s], 0x60u + 8u * (uint32_t)s + (uint32_t)STAGE);
         pha[s] ^= 1u;
@@ -1388,63 +1402,60 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       }
     }
   } else if (warp > VS_ROW_WARPS) {
-    // ---- gather producers: per (tile, view) pass, 128 rows x 3 thirds of a row's 18 float4 groups (feat64 groups [6j, 6j+6);
-    //      the last third: feat64 [12,16) + the 2 feat8 groups) = 384 items, 4 per thread; bilinear taps blended in fp32
-    //      (reference src/utils.py:74-89), packed to fp16 pairs, staged for the row warps' builds
+    // ---- gather producers.  A pass = one view of one tile: 128 rows x (16 feat64 + 2 feat8) float4 groups, bilinear taps blended
+    //      in fp32 (reference src/utils.py:74-89), packed to fp16 pairs, staged for the row warps' builds.  Work unit = 4 rows
+    //      (warp u % 7 takes unit u of 32): lane l works on row 4u + l / 8 and feat64 groups l % 8 and 8 + l % 8, so that the eight
+    //      lanes of a row read one 128-byte line per tap and load (lanes l % 8 < 2 also blend the row's two feat8 groups).
     if (nreal > 0) {
-      const int pt = (warp - VS_ROW_WARPS - 1) * 32 + lane;
+      const int pw = warp - VS_ROW_WARPS - 1, pt = pw * 32 + lane;
+      const int l8 = lane & 7, lr = lane >> 3;
       uint32_t phF[2] = {0u, 0u}, phG[3] = {0u, 0u, 0u}, phS[2] = {0u, 0u};
       int k = 0;
-      // this thread's items of a tile: sample ids, then positions (fetch_sample's arithmetic with 32-bit indices).  Both are loaded
-      // one tile ahead -- the ids under the view-0 gathers of the tile before, the positions under its view-1 gathers -- so that no
-      // tile starts with a chain of dependent global loads
-      auto load_ids = [&](int itn, int (&ids)[VS_ITEMS]) {
+      // Samples of a tile (threads 0..127: one row each): id, then position (fetch_sample's arithmetic with 32-bit indices), both
+      // loaded one tile ahead -- the id under the view-0 gathers of the tile before, the position under its view-1 gathers -- and
+      // staged in shared memory for the row warps AND for the other producer threads
+      const int srow = min(pt, 127);
+      auto load_id = [&](int itn) {
         const int tile = 2 * (cl + itn * ncl) + (int)rank;
-#pragma unroll
-        for (int j = 0; j < VS_ITEMS; ++j) {
-          const int si = tile * 128 + min((VS_ITEMS * pt + j) / 3, 127);
-          ids[j] = list[max(min(si, count - 1), 0)];
+        return list[max(min(tile * 128 + srow, count - 1), 0)];
+      };
+      auto load_pos = [&](int id, float (&pos)[3]) {
+        if (src.mode == 0) {
+          const int r = (int)((unsigned)id / (unsigned)src.S);
+          const float z = src.z ? src.z[id] : coarse_depth(src.ray_nf[2 * r], src.ray_nf[2 * r + 1], id - r * src.S, src.S);
+          pos[0] = src.o[0] + src.ray_d[3 * r + 0] * z;   // eval_pts = cam_pos + cam_rays * z  (reference src/model.py:1057)
+          pos[1] = src.o[1] + src.ray_d[3 * r + 1] * z;
+          pos[2] = src.o[2] + src.ray_d[3 * r + 2] * z;
+        } else {
+          pos[0] = src.pts[3ll * id + 0]; pos[1] = src.pts[3ll * id + 1]; pos[2] = src.pts[3ll * id + 2];
         }
       };
-      auto load_pos = [&](const int (&ids)[VS_ITEMS], float (&pos)[VS_ITEMS][3]) {
-#pragma unroll
-        for (int j = 0; j < VS_ITEMS; ++j) {
-          const int id = ids[j];
-          if (src.mode == 0) {
-            const int r = (int)((unsigned)id / (unsigned)src.S);
-            const float z = src.z ? src.z[id] : coarse_depth(src.ray_nf[2 * r], src.ray_nf[2 * r + 1], id - r * src.S, src.S);
-            pos[j][0] = src.o[0] + src.ray_d[3 * r + 0] * z;   // eval_pts = cam_pos + cam_rays * z  (reference src/model.py:1057)
-            pos[j][1] = src.o[1] + src.ray_d[3 * r + 1] * z;
-            pos[j][2] = src.o[2] + src.ray_d[3 * r + 2] * z;
-          } else {
-            pos[j][0] = src.pts[3ll * id + 0]; pos[j][1] = src.pts[3ll * id + 1]; pos[j][2] = src.pts[3ll * id + 2];
-          }
-        }
-      };
-      int idj[VS_ITEMS], idn[VS_ITEMS];
-      float pj[VS_ITEMS][3], pjn[VS_ITEMS][3];
-      load_ids(0, idj);
-      load_pos(idj, pj);
-#pragma unroll
-      for (int j = 0; j < VS_ITEMS; ++j) { idn[j] = idj[j]; pjn[j][0] = pj[j][0]; pjn[j][1] = pj[j][1]; pjn[j][2] = pj[j][2]; }
+      int idc = load_id(0), idn = idc;
+      float pc[3], pn[3];
+      load_pos(idc, pc);
+      pn[0] = pc[0]; pn[1] = pc[1]; pn[2] = pc[2];
+      const float4* const b64 = (const float4*)scs.f64.ptr;
+      const float4* const b8 = (const float4*)scs.f8.ptr;
+      const int hw64 = scs.f64.H * scs.f64.W, hw8 = scs.f8.H * scs.f8.W;
       for (int it = 0; it <= nreal; ++it) {
 #ifdef KPN_STAGE_TIMING
-        const bool vp_on = blockIdx.x == 0 && warp == VS_ROW_WARPS + 1 && it < TIM_TILES;
+        const bool vp_on = (int)blockIdx.x == tim_blk && warp == VS_ROW_WARPS + 1 && it < TIM_TILES;
 #endif
         VP(0);
-        // the thread that owns a row's first third stages the row's position and sample id for the row warps
         const int sb = it & 1;
         if (it >= 2) { tc::mbar_wait(&emptyS[sb], phS[sb], 0x88u + (uint32_t)sb); phS[sb] ^= 1u; }
+        uint32_t* const smp = stgS + sb * VS_SMP_WORDS;
+        if (pt < 128) {
+          smp[pt] = __float_as_uint(pc[0]); smp[128 + pt] = __float_as_uint(pc[1]); smp[256 + pt] = __float_as_uint(pc[2]);
+          smp[384 + pt] = (uint32_t)idc;
+          float pwv[3], sum = 0.0f;   // view weights (reference src/model.py:750-759; mask == 1 for shaded samples)
 #pragma unroll
-        for (int j = 0; j < VS_ITEMS; ++j) {
-          const int item = VS_ITEMS * pt + j, row = min(item / 3, 127);
-          if (item < 384 && item == 3 * row) {
-            uint32_t* sp = stgS + sb * VS_SMP_WORDS + row;
-            sp[0] = __float_as_uint(pj[j][0]); sp[128] = __float_as_uint(pj[j][1]); sp[256] = __float_as_uint(pj[j][2]);
-            sp[384] = (uint32_t)idj[j];
-          }
+          for (int vv = 0; vv < 3; ++vv) { const Proj q = project_s(scs, vv, pc); pwv[vv] = boundary_weight_fast(q); sum += pwv[vv]; }
+          const float inv = 1.0f / (sum + 1e-6f);
+#pragma unroll
+          for (int vv = 0; vv < 3; ++vv) smp[(4 + vv) * 128 + pt] = __float_as_uint(pwv[vv] * inv);
         }
-        __syncwarp();
+        tc::named_sync(5, VS_PROD_WARPS * 32);   // every producer reads the positions below
         if (lane == 0) tc::mbar_arrive(&fullS[sb]);
         VP(1);
         for (int v = 0; v < 3; ++v, ++k) {
@@ -1453,49 +1464,79 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
           if (k >= 3) { tc::mbar_wait(&emptyG[gb], phG[gb], 0x84u + (uint32_t)gb); phG[gb] ^= 1u; }
           VP(2 + 4 * v);
           if (it < nreal) {
-            if (v == 0) load_ids(it + 1, idn);
-            if (v == 1) load_pos(idn, pjn);
+            if (v == 0) idn = load_id(it + 1);
+            if (v == 1) load_pos(idn, pn);
           }
-          uint32_t* f64b = stg64 + fb * VS_F64_WORDS;
-          uint32_t* f8b = stg8 + gb * VS_F8_WORDS;
-#pragma unroll
-          for (int j = 0; j < VS_ITEMS; ++j) {
-            if (fake_gather) break;   // (timing experiment: stages nothing)
-            const int item = VS_ITEMS * pt + j, row = item / 3, third = item - 3 * row;
-            if (item >= 384) break;
+          uint32_t* const f64b = stg64 + fb * VS_F64_WORDS;
+          uint32_t* const f8b = stg8 + gb * VS_F8_WORDS;
+          // three rounds of loads per pass and warp: feat64 units (pw, pw + 7), (pw + 14, pw + 21) with 16 tap loads in flight
+          // per thread, then unit pw + 28 (warps 0..3) together with the feat8 groups of 16 rows (lane l: row 16 pw + l / 2,
+          // group l % 2; warp 4 also takes the eighth such block)
+          auto taps_of = [&](int row, int W, int H) {
+            const float p[3] = {u2f(smp[row]), u2f(smp[128 + row]), u2f(smp[256 + row])};
             float qu, qv;
-            vs_project_uv(scs, v, pj[j], qu, qv);
-            const Taps t64 = make_taps(qu, qv, scs.f64.W, scs.f64.H);
-            const int g0 = 6 * third;
-            {   // three float4 groups (12 tap loads in flight), then the other three: feat64, or feat64 group 15 + the feat8 pair
-              float f[12];
-              gather_f32<3>(scs.f64, v, t64, g0, f);
+            vs_project_uv(scs, v, p, qu, qv);
+            return make_taps(qu, qv, W, H);
+          };
+          auto load64 = [&](const Taps& t, float4 (&a)[4], float4 (&c)[4]) {
+            const float4* const q = b64 + (v * hw64) * 16 + l8;
+            a[0] = __ldg(q + t.o00 * 16); a[1] = __ldg(q + t.o01 * 16); a[2] = __ldg(q + t.o10 * 16); a[3] = __ldg(q + t.o11 * 16);
+            c[0] = __ldg(q + t.o00 * 16 + 8); c[1] = __ldg(q + t.o01 * 16 + 8);
+            c[2] = __ldg(q + t.o10 * 16 + 8); c[3] = __ldg(q + t.o11 * 16 + 8);
+          };
+          auto blend2 = [&](const Taps& t, const float4 (&a)[4], uint32_t& w0, uint32_t& w1) {
+            w0 = tc::pack_h2(a[0].x * t.w00 + a[1].x * t.w01 + a[2].x * t.w10 + a[3].x * t.w11,
+                             a[0].y * t.w00 + a[1].y * t.w01 + a[2].y * t.w10 + a[3].y * t.w11);
+            w1 = tc::pack_h2(a[0].z * t.w00 + a[1].z * t.w01 + a[2].z * t.w10 + a[3].z * t.w11,
+                             a[0].w * t.w00 + a[1].w * t.w01 + a[2].w * t.w10 + a[3].w * t.w11);
+          };
+          auto store64 = [&](int row, const Taps& t, const float4 (&a)[4], const float4 (&c)[4]) {
+            uint32_t* const d = f64b + (2 * l8) * 128 + (row ^ (4 * l8));   // words 2g, 2g + 1 for g = l8, 8 + l8: see vs_f64_word
+            uint32_t w0, w1;
+            blend2(t, a, w0, w1);
+            d[0] = w0; d[128] = w1;
+            blend2(t, c, w0, w1);
+            d[16 * 128] = w0; d[17 * 128] = w1;
+          };
+          if (!fake_gather) {
 #pragma unroll
-              for (int i = 0; i < 6; ++i) f64b[(2 * g0 + i) * 128 + row] = tc::pack_h2(f[2 * i], f[2 * i + 1]);
+            for (int rd = 0; rd < 2; ++rd) {
+              const int ra = 4 * (pw + 14 * rd) + lr, rb = ra + 28;
+              const Taps ta = taps_of(ra, scs.f64.W, scs.f64.H), tb = taps_of(rb, scs.f64.W, scs.f64.H);
+              float4 a[4], c[4], e[4], f[4];
+              load64(ta, a, c);
+              load64(tb, e, f);
+              store64(ra, ta, a, c);
+              store64(rb, tb, e, f);
             }
-            if (third < 2) {
-              float f[12];
-              gather_f32<3>(scs.f64, v, t64, g0 + 3, f);
-#pragma unroll
-              for (int i = 0; i < 6; ++i) f64b[(2 * (g0 + 3) + i) * 128 + row] = tc::pack_h2(f[2 * i], f[2 * i + 1]);
-            } else {
-              float f[4], g8[8];
-              const Taps t8 = make_taps(qu, qv, scs.f8.W, scs.f8.H);
-              gather_f32<1>(scs.f64, v, t64, 15, f);
-              gather_f32<2>(scs.f8, v, t8, 0, g8);
-              f64b[30 * 128 + row] = tc::pack_h2(f[0], f[1]);
-              f64b[31 * 128 + row] = tc::pack_h2(f[2], f[3]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) f8b[i * 128 + row] = tc::pack_h2(g8[2 * i], g8[2 * i + 1]);
+            {
+              const int r8 = 16 * pw + (lane >> 1), r8b = 112 + (lane >> 1), g8 = lane & 1;
+              const Taps t8 = taps_of(r8, scs.f8.W, scs.f8.H);
+              const float4* const q8 = b8 + (v * hw8) * 2 + g8;
+              float4 e[4] = {__ldg(q8 + t8.o00 * 2), __ldg(q8 + t8.o01 * 2), __ldg(q8 + t8.o10 * 2), __ldg(q8 + t8.o11 * 2)};
+              uint32_t w0, w1;
+              if (pw < 4) {
+                const int rc = 4 * (pw + 28) + lr;
+                const Taps tc64 = taps_of(rc, scs.f64.W, scs.f64.H);
+                float4 a[4], c[4];
+                load64(tc64, a, c);
+                store64(rc, tc64, a, c);
+              } else if (pw == 4) {
+                const Taps t8b = taps_of(r8b, scs.f8.W, scs.f8.H);
+                const float4 h[4] = {__ldg(q8 + t8b.o00 * 2), __ldg(q8 + t8b.o01 * 2), __ldg(q8 + t8b.o10 * 2), __ldg(q8 + t8b.o11 * 2)};
+                blend2(t8b, h, w0, w1);
+                f8b[(2 * g8) * 128 + r8b] = w0; f8b[(2 * g8 + 1) * 128 + r8b] = w1;
+              }
+              blend2(t8, e, w0, w1);
+              f8b[(2 * g8) * 128 + r8] = w0; f8b[(2 * g8 + 1) * 128 + r8] = w1;
             }
-            VP(3 + 4 * v + j);
           }
+          VP(3 + 4 * v);
           __syncwarp();
           if (lane == 0) { tc::mbar_arrive(&fullF[fb]); tc::mbar_arrive(&fullG[gb]); }   // release: the warp's staged words are visible
           VP(5 + 4 * v);
         }
-#pragma unroll
-        for (int j = 0; j < VS_ITEMS; ++j) { idj[j] = idn[j]; pj[j][0] = pjn[j][0]; pj[j][1] = pjn[j][1]; pj[j][2] = pjn[j][2]; }
+        idc = idn; pc[0] = pn[0]; pc[1] = pn[1]; pc[2] = pn[2];
       }
     }
   } else if (nreal > 0) {
@@ -1524,7 +1565,7 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       const int fb = k & 1;
       tc::mbar_wait(&fullF[fb], fphF[fb], 0x90u + (uint32_t)fb);
       fphF[fb] ^= 1u;
-      return stg64 + fb * VS_F64_WORDS + row;
+      return stg64 + fb * VS_F64_WORDS;
     };
     auto feat64_done = [&](int k) {   // after the build has copied them: hand the buffer back
       __syncwarp();
@@ -1547,17 +1588,13 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       fphS[sb] ^= 1u;
       const uint32_t* sp = stgS + sb * VS_SMP_WORDS + row;
       cur.si = tile * 128 + row;
+      cur.row = row;
       cur.live = cur.si < count;
       cur.p[0] = u2f(sp[0]); cur.p[1] = u2f(sp[128]); cur.p[2] = u2f(sp[256]);
       cur.id = (int)sp[384];
+      cur.pw[0] = u2f(sp[512]); cur.pw[1] = u2f(sp[640]); cur.pw[2] = u2f(sp[768]);
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&emptyS[sb]);
-      float sum = 0.0f;   // view weights (reference src/model.py:750-759; mask == 1 for shaded samples)
-#pragma unroll
-      for (int v = 0; v < 3; ++v) { const Proj q = project_s(scs, v, cur.p); cur.pw[v] = boundary_weight_fast(q); sum += cur.pw[v]; }
-      const float inv = 1.0f / (sum + 1e-6f);
-#pragma unroll
-      for (int v = 0; v < 3; ++v) cur.pw[v] *= inv;
       vs_build<NK>(scs, cur, 0, cq, A1, feat64_of(3 * itn));
       feat64_done(3 * itn);
       vs_signal(cx, 1, lane);
@@ -1565,7 +1602,7 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
     start_tile(0);
     for (int it = 0; it <= nreal; ++it) {
 #ifdef KPN_STAGE_TIMING
-      const bool vt_on = blockIdx.x == 0 && warp == 0 && it < TIM_TILES;
+      const bool vt_on = (int)blockIdx.x == tim_blk && warp == 0 && it < TIM_TILES;
 #endif
       VT(0);
       const int k0 = 3 * it;
@@ -1717,12 +1754,15 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
       if (it < nreal) { start_tile(it + 1);   VT(29); }
     }
 #ifdef KPN_STAGE_TIMING
-    if (blockIdx.x == 0 && warp == 0 && lane == 0) { kpn_tim_tile[0] = min(nreal + 1, TIM_TILES); kpn_tim_tile[1] = kpn_tim_tile[0]; }
+    if ((int)blockIdx.x == tim_blk && warp == 0 && lane == 0) { kpn_tim_tile[0] = min(nreal + 1, TIM_TILES); kpn_tim_tile[1] = kpn_tim_tile[0]; }
 #endif
     vs_wait(cx, 0);   // the last (ghost) view-2 stage: tensor memory must be idle before it is released
   }
   tc::fence_before_sync();
   __syncthreads();
+#ifdef KPN_STAGE_TIMING
+  if (t == 0 && blockIdx.x < 256) kpn_tim[3 * TIM_TILES * TIM_WORDS + blockIdx.x] = (unsigned long long)(clock64() - blk_t0);
+#endif
   tc::cluster_sync_all();
   if (warp == 0) tc::tmem_dealloc2(tbase, 512);
 }
@@ -1822,7 +1862,11 @@ static cudaError_t launch_tc_impl(const DevScene* sc, const TcConsts& C, const u
     long long vp = (vt + 1) / 2;
     const int vgrid = 2 * (int)(vp < 1 ? 1 : (vp > max_clusters ? max_clusters : vp));
 #ifdef KPN_STAGE_TIMING   // instrumented build only: producers skip the gathers (garbage output; measures the pipeline's floor)
-    static const int fake = [] { const char* e = getenv("KPN_VS_FAKE"); return e && e[0] == '1' ? 1 : 0; }();
+    static const int fake = [] {   // bits 0-7: KPN_VS_FAKE; bits 8+: the block whose warps are stamped (KPN_TIM_BLOCK, even = leader CTA)
+      const char* e = getenv("KPN_VS_FAKE");
+      const char* b = getenv("KPN_TIM_BLOCK");
+      return (e && e[0] == '1' ? 1 : 0) | ((b ? atoi(b) : 0) << 8);
+    }();
 #else
     const int fake = 0;
 #endif
@@ -1893,7 +1937,7 @@ cudaError_t tc_stage_times(unsigned long long* out, int n_words, int* n_tiles) {
   e = cudaMemcpyFromSymbol(nt, kpn_tim_tile, sizeof(nt));
   if (e != cudaSuccess) return e;
   *n_tiles = nt[0] < nt[1] ? nt[0] : nt[1];
-  const size_t bytes = sizeof(unsigned long long) * (size_t)(n_words < 3 * TIM_TILES * TIM_WORDS ? n_words : 3 * TIM_TILES * TIM_WORDS);
+  const size_t bytes = sizeof(unsigned long long) * (size_t)(n_words < 3 * TIM_TILES * TIM_WORDS + 256 ? n_words : 3 * TIM_TILES * TIM_WORDS + 256);
   e = cudaMemcpyFromSymbol(out, kpn_tim, bytes);
   if (e != cudaSuccess) return e;
   const int zero[2] = {0, 0};
