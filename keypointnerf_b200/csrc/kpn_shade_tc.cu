@@ -1176,7 +1176,7 @@ shade_geo_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcCon
 // exchange area of the four column quarters' partial density sums); stream B: activations [288,384), accumulator [384,512).
 constexpr int VS_A0 = 0, VS_D0 = 160, VS_A1 = 288, VS_D1 = 384;
 constexpr int VS_ROW_WARPS = 16;
-constexpr int VS_PROD_WARPS = 7;                              // gather producers (24 warps x 80 registers)
+constexpr int VS_PROD_WARPS = 7;                              // gather producers (24 warps launched with 80 registers: row warps 72, the rest 96)
 constexpr int VS_THREADS = (VS_ROW_WARPS + 1 + VS_PROD_WARPS) * 32;
 // Gather staging: the producer warps blend the bilinear taps of every (row, view) pass into shared memory as packed fp16 pairs
 // (32 feat64 words + 4 feat8 words per row; feat64 word w of row r at vs_f64_word(w, r), feat8 word w at [w * 128 + r]); the row
@@ -1303,7 +1303,7 @@ __device__ __forceinline__ void vs_accumulate(uint32_t d, float pw, float (&s1)[
 }
 
 template <int NK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(VS_THREADS, 1)   // 17 warps are allocated as 20: 96 registers per thread
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(VS_THREADS, 1)   // 24 warps x 80 registers, redistributed by setmaxnreg
 shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ TcConsts C, const uint8_t* __restrict__ wpair,
                       int two_term, SampleSrc src, const int* __restrict__ list, const int* __restrict__ count_ptr,
                       int query_mode, ShadeOut so, uint4* __restrict__ lat_out, int fake_gather) {

@@ -53,14 +53,14 @@ KEEP = ["gpu__time_duration.sum", "launch__", "smsp__inst_executed.sum", "smsp__
         "sm__throughput.avg", "sm__warps_active.avg"]
 
 
-def ncu_kernel(name, kern_sub, fn_name):
+def ncu_kernel(name, kern_sub):
     rep = os.path.join(G, f"{tag}_{name}.ncu-rep")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, val = rows[0], rows[1], rows[2]
     traffic = {}
     with open(os.path.join(P, f"{outp}_ncu_{name}_metrics.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none, one launch of shade_{name}_kernel<18> inside bench.py (one chunk = the whole 512x512x128 frame)\n")
+        f.write(f"# ncu --set full --clock-control none, one launch of {kern_sub[:-5]}<18> inside bench.py (one chunk = the whole 512x512x128 frame)\n")
         for h, u, v in zip(hdr, units, val):
             if any(k in h for k in KEEP) and ".max" not in h and ".min" not in h and ".sum.pct" not in h:
                 f.write(f"{h:95s} {v:>20s} {u}\n")
@@ -69,19 +69,33 @@ def ncu_kernel(name, kern_sub, fn_name):
                 x *= {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}.get(u, 1)
                 traffic[h] = x
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    open("/tmp/_src.csv", "w").write(src)
+    src_csv = f"/tmp/_src_{name}.csv"
+    open(src_csv, "w").write(src)
     cub = "/tmp/_cub"
     os.makedirs(cub, exist_ok=True)
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "keypointnerf_b200/lib/libkpnerf_b200.so")], cwd=cub, capture_output=True)
     sass = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(cub, "kpn_shade_tc.sm_100a.cubin")], capture_output=True, text=True).stdout
     open("/tmp/_tci.sass", "w").write(sass)
     lines = open(os.path.join(ROOT, "keypointnerf_b200/csrc/kpn_shade_tc.cu")).read().splitlines()
-    lo = next(i + 1 for i, l in enumerate(lines) if l.startswith("__device__ __forceinline__ void " + fn_name))
-    hi = next(i + 1 for i in range(lo, len(lines)) if lines[i] == "}")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools/ncu_by_line.py"), "/tmp/_src.csv", "/tmp/_tci.sass", kern_sub, "kpn_shade_tc.cu",
-                          str(lo), str(hi)], capture_output=True, text=True).stdout
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools/ncu_by_line.py"), src_csv, "/tmp/_tci.sass", kern_sub, "kpn_shade_tc.cu",
+                          "1", str(len(lines))], capture_output=True, text=True).stdout
+    rows = []
+    head = []
+    for l in out.splitlines():
+        mm = re.match(r"\s*(-?\d+)\s+([\d.]+)\s+([\d.]+)\s+(\d+)\s*(.*)", l)
+        if mm:
+            rows.append((int(mm[1]), float(mm[2]), float(mm[3]), int(mm[4]), mm[5]))
+        else:
+            head.append(l)
+    rows.sort(key=lambda r: -r[1])
     with open(os.path.join(P, f"{outp}_ncu_{name}_by_line.txt"), "w") as f:
-        f.write(f"# {fn_name}: kpn_shade_tc.cu lines {lo}-{hi} (line -1 = code outside the tile function: issuer warp, prologue)\n" + out)
+        f.write(f"# {kern_sub}: warp instructions / stall samples per source line of kpn_shade_tc.cu (innermost inlined frame), lines with\n"
+                "# >= 0.25 % of the instructions, heaviest first (line -1: no line info)\n" + "\n".join(head[:2]) + "\n")
+        for r in rows:
+            if r[1] < 0.25:
+                break
+            text = lines[r[0] - 1].strip()[:90] if r[0] > 0 else ""
+            f.write(f"{r[0]:6d} {r[1]:6.2f} {r[2]:6.2f} {r[3]:6d}  {r[4][:60]:60s} | {text}\n")
     return traffic
 
 
@@ -108,7 +122,7 @@ def frame_dram():
 
 
 launches()
-tr = {"geo": ncu_kernel("geo", "shade_geo_kernelILi18", "geo_tile"), "color": ncu_kernel("color", "shade_color_kernelILi18", "color_tile")}
+tr = {"geo": ncu_kernel("geo", "shade_geo_vseq_kernelILi18"), "color": ncu_kernel("color", "shade_color_kernelILi18")}
 fr = frame_dram()
 tot = sum(v.get("dram__bytes_read.sum", 0) + v.get("dram__bytes_write.sum", 0) for v in fr.values())
 json.dump({"source": f"ncu captures gpurun_out/{tag}_*: `kernels` = one --set full launch of each shading kernel (a launch covers one chunk = the whole "
