@@ -1,6 +1,6 @@
 #!/bin/bash
 # Multi-GPU pass on N GPUs of one box: the N-GPU == 1-GPU bit-identity check, then the bench at N for configs 2 (= 5: one view per
-# GPU, weak scaling) and 4 (one 1024^2 frame in lattice phases, strong scaling) and the reference arm.  Usage: tools/gpu_multi.sh <tag> <N>
+# GPU, weak scaling) and 4 (one 1024^2 frame in lattice phases, strong scaling) and the reference arm.  Usage: tools/gpu_multi.sh <tag> <N> [noref]
 tag=${1:-mg}; N=${2:-2}
 out=gpurun_out
 mkdir -p $out
@@ -19,4 +19,4 @@ except Exception as e:
     print("N=$N cfg $cfg FAILED", e); print(open("$out/${tag}_n${N}_c${cfg}.err").read()[-2000:])
 PY
 done
-timeout 400 $TR --master-port 29630 bench.py --gpus $N --steps 5 --warmup 1 --impl reference > $out/${tag}_n${N}_ref.json 2> $out/${tag}_n${N}_ref.err; cat $out/${tag}_n${N}_ref.json | cut -c1-300
+[ "$3" = noref ] || timeout 400 $TR --master-port 29630 bench.py --gpus $N --steps 5 --warmup 1 --impl reference > $out/${tag}_n${N}_ref.json 2> $out/${tag}_n${N}_ref.err; cat $out/${tag}_n${N}_ref.json | cut -c1-300
