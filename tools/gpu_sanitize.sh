@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer memcheck over the smoke render (tensor-core engine, coarse + fine) and a small fp32-engine / query / ERT run.
 out=gpurun_out; mkdir -p $out
-timeout 600 compute-sanitizer --tool memcheck --leak-check no --error-exitcode 3 python -c "
+timeout 280 compute-sanitizer --tool memcheck --leak-check no --error-exitcode 3 python -c "
 import __graft_entry__ as g
 g.smoke()
 import torch
