@@ -304,6 +304,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    import gc
+    gc.collect()
+    gc.disable()   # no collector pauses inside the timed loops (timeit does the same); re-enabled below
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -352,6 +355,7 @@ def main():
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    gc.enable()
     e2e_val = rays_per_step * args.steps / float(te.item())
     h2d = sum(int(t.numel() * t.element_size()) for t in
               [h["feat_geo"][0], h["feat_geo"][1], h["feat_tex"], h["img"], h["fg"], h["cam"]["KRT"], h["sp_data"]["extrin"],
@@ -399,7 +403,7 @@ def main():
                 "vs_baseline": None, "dtype": "fp32" if args.engine == 1 else net.marcher_dtype(), "data": "synthetic",
                 "config": {"workload": cfg["workload"], "baseline_config": args.config, "parallelism": part,
                            "scene": f"{args.scene} foreground masks", "n_kpt": n_kpt,
-                           "l2": "flushed between timed iterations (256 MiB write)", "engine": args.engine,
+                           "l2": "flushed between timed iterations (256 MiB write)", "gc": "python collector off inside the timed loops", "engine": args.engine,
                            "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
