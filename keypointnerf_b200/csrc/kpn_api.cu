@@ -59,7 +59,7 @@ struct kpn_ctx {
   DevBuf wbuf;
   DevBuf wblob;                // fp16 weight tiles of the tensor-core engine (core-matrix layout)
   DevBuf wlo;                  // per-CTA-rank half-blobs [W_hi halves | W_lo halves] of the geometry stages (CTA-pair kernel)
-  DevBuf wlo_vs;               // the same for the view-sequential kernel (engine 3: different layer-0 input permutation)
+  DevBuf wlo_vs;               // the same for the view-sequential kernel (different layer-0 input permutation)
   TcConsts tcc;                // fp32 constants of the tensor-core engine (kernel parameter)
   bool tc_weights = false;
   int scene_views = 0;
@@ -246,7 +246,7 @@ extern "C" int kpn_set_weights(kpn_ctx* c, const kpn_weights* w) {
     const size_t geo_bytes = tc_weight_lo_bytes(w->n_kpt);          // bytes of the full W_hi tiles of stages 0..5
     std::vector<__half> pair(tc_pair_blob_bytes(w->n_kpt) / 2, __float2half_rn(0.0f));   // [rank][hi halves | lo halves]
     const bool vseq = vs_run_cols(w->n_kpt) > 0;
-    std::vector<__half> pair_vs(vseq ? pair.size() : 0, __float2half_rn(0.0f));           // engine 3: same tiles, other K permutation
+    std::vector<__half> pair_vs(vseq ? pair.size() : 0, __float2half_rn(0.0f));           // view-sequential kernel: same tiles, other K permutation
     // stage -> (layer, first row in the tile); stage 4 stacks the density layer 0 and the colour compress layer
     const int stage_layer[TC_NSTAGE] = {L_GEO0, L_GEO1, L_GEO2, L_GEO3, L_DEN0, L_DEN1, L_BASE0, L_BASE1, L_VIS1A, L_VIS1B, L_VIS2A, L_OUT0, L_RE1};
     auto put_pair = [&](std::vector<__half>& dst, int stage, int n, int kk, float wv) {

@@ -1613,7 +1613,6 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
         vs_accumulate(D0 + c16, prev_pw2, s1, s2);
       }
       // A: pooling of the previous tile: mean = S1, var = S2 - S1^2 (2 - sum pw) (== sum pw (x - mean)^2), two fp16 terms each
-   
       {
         uint32_t mh[8], vh[8], ml[8], vl[8];
         const float k = 2.0f - prev_s0;
@@ -1898,7 +1897,7 @@ cudaError_t launch_shade_tc(const DevScene* sc, const TcConsts& C, const uint8_t
                             const SampleSrc& src, const int* list, const int* counter, long long n_max, int query_mode,
                             const ShadeOut& so, void* lat_scratch, void* list2, int* count2, int num_sms, cudaEvent_t after_geo,
                             cudaStream_t st) {
-  if (n_kpt == -18)   // view-sequential geometry kernel (engine 3)
+  if (n_kpt == -18)   // view-sequential geometry kernel (kpn_api.cu negates n_kpt to select it)
     return launch_tc_impl<18, true>(sc, C, wblob, wpair, two_term, src, list, counter, n_max, query_mode, so, (uint4*)lat_scratch,
                                     (int2*)list2, count2, num_sms, after_geo, st);
   if (n_kpt == 18)

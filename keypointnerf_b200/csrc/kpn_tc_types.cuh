@@ -61,7 +61,7 @@ __host__ __device__ constexpr int tc_kbias(int stage, int n_kpt) {
   }
 }
 
-// ---- "view-sequential" geometry kernel (engine 3, 18 keypoints): a row is a SAMPLE, its three views are run through
+// ---- "view-sequential" geometry kernel (18 keypoints; engines 0 and 3): a row is a SAMPLE, its three views are run through
 // stages 0-3 one after the other, FOUR threads build / post-process a row (column quarters).  Layer-0 input of one
 // (sample, view): 96 packed columns = 4 runs of 24: threads 0-2: two keypoint pairs (14 columns) + five float4 groups of feat64
 // (10 columns); thread 3: three pairs (21) + one group (2) + the bias column.
