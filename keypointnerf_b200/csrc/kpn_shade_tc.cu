@@ -1363,6 +1363,10 @@ shade_geo_vseq_kernel(const DevScene* __restrict__ scp, const __grid_constant__ 
 #endif
   // registers: the row warps hand 8 per thread to the issuer / producer warps, whose gathers keep 16 tap loads (64 registers) in
   // flight per thread -- global-memory latency times loads in flight is what bounds the producers
+  static_assert(VS_ROW_WARPS % 4 == 0 && (VS_THREADS / 32) % 4 == 0 &&
+                VS_ROW_WARPS * 72 + (VS_THREADS / 32 - VS_ROW_WARPS) * 96 <= (VS_THREADS / 32) * 80,
+                "whole warpgroups change their budget, and what the producers take the row warps must have released (else the "
+                "allocation spins forever)");
   if (warp < VS_ROW_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   else asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
   if (warp == VS_ROW_WARPS) {
